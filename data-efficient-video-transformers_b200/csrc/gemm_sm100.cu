@@ -1,0 +1,487 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with a fused epilogue (see include/tvt.h: tvt_gemm).
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0 (one lane)  TMA producer: global -> 128B-swizzled smem ring, mbarrier complete_tx
+//   warp 1 (one lane)  MMA issuer:   tcgen05.mma 128 x BN x 16, fp32 accumulators in tensor memory,
+//                                    tcgen05.commit releases smem stages / publishes accumulators
+//   warp 2             TMEM allocator (alloc at start, dealloc at end)
+//   warps 4..7         epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused math -> global
+// Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Work item = (split, m_block, n_block); split-K partials are combined with red.global.add.f32.
+// Operand storage is selected per operand (K-major or MN-major) through the UMMA descriptors, so the
+// forward (X W^T), dgrad (dY W) and wgrad (dY^T X) products all read the tensors as torch stores them.
+#include <cuda.h>
+#include <mutex>
+
+#include "tvt_common.cuh"
+#include "tvt_ptx.cuh"
+
+namespace tvt {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 256;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct Params {
+  int M, N, K, splits;
+  int act;
+  float alpha;
+  const float* bias;
+  const void* residual; int residual_f32; long long ld_residual;
+  const void* relu_mask; int mask_f32; long long ld_mask;
+  const void* gelu_gate; int gate_f32; long long ld_gate;
+  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+  void* out_preact; int preact_f32; long long ld_preact;
+  float* out_f32; long long ld_f32; int atomic_out;
+  __nv_bfloat16* out_bf16; __nv_bfloat16* out_bf16_lo; long long ld_bf16;
+  unsigned mn_lbo, mn_sbo;  // MN-major descriptor strides (bring-up knob, see tvt_debug_set_mn_desc)
+};
+
+static unsigned g_mn_lbo = BK * 128, g_mn_sbo = 1024;
+
+template <int BN, int kPlanes>
+struct Cfg {
+  static constexpr int kAPlane = BM * BK * 2;
+  static constexpr int kBPlane = BN * BK * 2;
+  static constexpr int kStageBytes = kPlanes * (kAPlane + kBPlane);
+  static constexpr int kStages = (kSmemLimit - 2048) / kStageBytes;
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = kAccStages * BN;  // 512 or 256: powers of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(kStages >= 2, "need at least a double buffer");
+  static_assert(kSmemBytes <= kSmemLimit, "smem budget");
+};
+
+__device__ __forceinline__ void load8(const void* base, int is_f32, long long off, float (&v)[8]) {
+  if (is_f32) {
+    const float* p = reinterpret_cast<const float*>(base) + off;
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    Vec16<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(base) + off, v);
+  }
+}
+__device__ __forceinline__ void store8(void* base, int is_f32, long long off, const float (&v)[8]) {
+  if (is_f32) {
+    float* p = reinterpret_cast<float*>(base) + off;
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(base) + off, v);
+  }
+}
+
+// Fused epilogue on 8 consecutive columns of one output row.
+__device__ __forceinline__ void epilogue8(const Params& p, long long row, int col, float (&v)[8]) {
+  if (p.atomic_out) {
+    float* dst = p.out_f32 + row * p.ld_f32 + col;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0] * p.alpha),
+                 "f"(v[1] * p.alpha), "f"(v[2] * p.alpha), "f"(v[3] * p.alpha)
+                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4] * p.alpha),
+                 "f"(v[5] * p.alpha), "f"(v[6] * p.alpha), "f"(v[7] * p.alpha)
+                 : "memory");
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+  if (p.bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (p.out_preact) store8(p.out_preact, p.preact_f32, row * p.ld_preact + col, v);
+  if (p.act == TVT_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+  } else if (p.act == TVT_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_f(v[i]);
+  }
+  if (p.relu_mask) {
+    float m[8];
+    load8(p.relu_mask, p.mask_f32, row * p.ld_mask + col, m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = m[i] > 0.0f ? v[i] : 0.0f;
+  }
+  if (p.gelu_gate) {
+    float g[8];
+    load8(p.gelu_gate, p.gate_f32, row * p.ld_gate + col, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= gelu_grad_f(g[i]);
+  }
+  if (p.dropout_thr16) {
+    const unsigned long long e = static_cast<unsigned long long>(row) * p.N + col;
+    const uint64_t b0 = dropout_bits4(p.dropout_seed, e >> 2);
+    const uint64_t b1 = dropout_bits4(p.dropout_seed, (e >> 2) + 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = dropout_keep_lane(b0, i, p.dropout_thr16) ? v[i] * p.dropout_scale : 0.0f;
+      v[4 + i] = dropout_keep_lane(b1, i, p.dropout_thr16) ? v[4 + i] * p.dropout_scale : 0.0f;
+    }
+  }
+  if (p.residual) {
+    float r[8];
+    load8(p.residual, p.residual_f32, row * p.ld_residual + col, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+  }
+  if (p.out_f32) store8(p.out_f32, 1, row * p.ld_f32 + col, v);
+  if (p.out_bf16) {
+    float hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hi[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+    Vec16<__nv_bfloat16>::store(p.out_bf16 + row * p.ld_bf16 + col, hi);
+    if (p.out_bf16_lo) {
+      float lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) lo[i] = v[i] - hi[i];
+      Vec16<__nv_bfloat16>::store(p.out_bf16_lo + row * p.ld_bf16 + col, lo);
+    }
+  }
+}
+
+template <int BN, bool kAMN, bool kBMN, int kPlanes>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+            const Params p) {
+  using C = Cfg<BN, kPlanes>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* tfull_bar = bars + 2 * C::kStages;
+  uint64_t* tempty_bar = tfull_bar + C::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + C::kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < C::kAccStages; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int total = num_m * num_n * p.splits;
+  const int kb_total = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int n_blk = w % num_n;
+        const int t = w / num_n;
+        const int m_blk = t % num_m;
+        const int split = t / num_m;
+        const int kb0 = static_cast<int>(static_cast<long long>(split) * kb_total / p.splits);
+        const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, C::kStageBytes);
+          uint8_t* st = smem + stage * C::kStageBytes;
+#pragma unroll
+          for (int pl = 0; pl < kPlanes; ++pl) {
+            const CUtensorMap* ma = pl == 0 ? &tmA : &tmAlo;
+            const CUtensorMap* mb = pl == 0 ? &tmB : &tmBlo;
+            const uint32_t sa = smem_u32(st + pl * C::kAPlane);
+            const uint32_t sb = smem_u32(st + kPlanes * C::kAPlane + pl * C::kBPlane);
+            if constexpr (!kAMN) {
+              tma_load_2d(sa, ma, fb, kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sa + j * (BK * 128), ma, fb, m_blk * BM + j * 64, kb * BK);
+            }
+            if constexpr (!kBMN) {
+              tma_load_2d(sb, mb, fb, kb * BK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * (BK * 128), mb, fb, n_blk * BN + j * 64, kb * BK);
+            }
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, kAMN, kBMN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int split = (w / num_n) / num_m;
+        const int kb0 = static_cast<int>(static_cast<long long>(split) * kb_total / p.splits);
+        const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
+        mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        uint32_t accumulate = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          uint8_t* st = smem + stage * C::kStageBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // plane pairs: (hi,hi) always; (hi,lo) and (lo,hi) in the 3-pass fp32-accurate mode
+#pragma unroll
+            for (int pr = 0; pr < (kPlanes == 1 ? 1 : 3); ++pr) {
+              const int pa = (pr == 2) ? 1 : 0;
+              const int pb = (pr == 1) ? 1 : 0;
+              const uint32_t sa = smem_u32(st + pa * C::kAPlane);
+              const uint32_t sb = smem_u32(st + kPlanes * C::kAPlane + pb * C::kBPlane);
+              const uint64_t adesc = kAMN ? make_smem_desc_sw128(sa + k * 16 * 128, p.mn_lbo, p.mn_sbo)
+                                          : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+              const uint64_t bdesc = kBMN ? make_smem_desc_sw128(sb + k * 16 * 128, p.mn_lbo, p.mn_sbo)
+                                          : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+              tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(smem_u32(&tfull_bar[as]));
+        if (++as == C::kAccStages) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int n_blk = w % num_n;
+      const int m_blk = (w / num_n) % num_m;
+      const int split = (w / num_n) / num_m;
+      const int kb0 = static_cast<int>(static_cast<long long>(split) * kb_total / p.splits);
+      const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
+      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+      tc_fence_after();
+      const long long row = static_cast<long long>(m_blk) * BM + ew * 32 + lane;
+      const bool row_ok = row < p.M && kb1 > kb0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.N) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              epilogue8(p, row, col, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+      if (++as == C::kAccStages) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map with 128B swizzle: dims {inner, outer}, row pitch ld elements.
+static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld,
+                    int box_inner, int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return TVT_ECUDA;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld)",
+                   static_cast<int>(r), inner, outer, ld);
+    return TVT_ECUDA;
+  }
+  return TVT_OK;
+}
+
+template <int BN, bool kAMN, bool kBMN, int kPlanes>
+static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) {
+  using C = Cfg<BN, kPlanes>;
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  int rc;
+  auto mapA = [&](CUtensorMap* m, const void* ptr) {
+    return kAMN ? make_map(m, ptr, a->m, a->k, a->lda, 64, BK) : make_map(m, ptr, a->k, a->m, a->lda, BK, BM);
+  };
+  auto mapB = [&](CUtensorMap* m, const void* ptr) {
+    return kBMN ? make_map(m, ptr, a->n, a->k, a->ldb, 64, BK) : make_map(m, ptr, a->k, a->n, a->ldb, BK, BN);
+  };
+  if ((rc = mapA(&tmA, a->a)) != TVT_OK) return rc;
+  if ((rc = mapB(&tmB, a->b)) != TVT_OK) return rc;
+  if (kPlanes == 2) {
+    if ((rc = mapA(&tmAlo, a->a_lo)) != TVT_OK) return rc;
+    if ((rc = mapB(&tmBlo, a->b_lo)) != TVT_OK) return rc;
+  } else {
+    tmAlo = tmA;
+    tmBlo = tmB;
+  }
+  auto kern = gemm_kernel<BN, kAMN, kBMN, kPlanes>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) {
+    set_last_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(attr_err));
+    return TVT_ECUDA;
+  }
+  const long long num_m = (a->m + BM - 1) / BM, num_n = (a->n + BN - 1) / BN;
+  const long long total = num_m * num_n * p.splits;
+  const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, p);
+  return check_launch("tvt_gemm");
+}
+
+template <int BN, int kPlanes>
+static int dispatch_major(const tvt_gemm_args* a, const Params& p, cudaStream_t s) {
+  if (!a->a_mn_major && !a->b_mn_major) return launch<BN, false, false, kPlanes>(a, p, s);
+  if (!a->a_mn_major && a->b_mn_major) return launch<BN, false, true, kPlanes>(a, p, s);
+  if (a->a_mn_major && a->b_mn_major) return launch<BN, true, true, kPlanes>(a, p, s);
+  return launch<BN, true, false, kPlanes>(a, p, s);
+}
+
+}  // namespace gemm
+}  // namespace tvt
+
+// Bring-up hook (not part of include/tvt.h): override the MN-major descriptor byte offsets.
+extern "C" void tvt_debug_set_mn_desc(unsigned lbo, unsigned sbo) {
+  tvt::gemm::g_mn_lbo = lbo;
+  tvt::gemm::g_mn_sbo = sbo;
+}
+
+extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr, "tvt_gemm: null args");
+  TVT_REQUIRE(a->a && a->b, "tvt_gemm: null operand");
+  TVT_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, "tvt_gemm: m, n, k must be positive (got %lld %lld %lld)",
+              (long long)a->m, (long long)a->n, (long long)a->k);
+  TVT_REQUIRE(a->m < (1ll << 31) && a->n < (1ll << 31) && a->k < (1ll << 31), "tvt_gemm: dims exceed int32");
+  TVT_REQUIRE((a->a_lo == nullptr) == (a->b_lo == nullptr), "tvt_gemm: a_lo and b_lo must be given together");
+  TVT_REQUIRE(a->n % 8 == 0, "tvt_gemm: n must be a multiple of 8 (got %lld)", (long long)a->n);
+  TVT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "tvt_gemm: lda/ldb must be multiples of 8 elements");
+  TVT_REQUIRE(a->lda >= (a->a_mn_major ? a->m : a->k), "tvt_gemm: lda too small");
+  TVT_REQUIRE(a->ldb >= (a->b_mn_major ? a->n : a->k), "tvt_gemm: ldb too small");
+  TVT_REQUIRE(!(a->a_mn_major && a->m % 8) && !(!a->a_mn_major && a->k % 8) && !(!a->b_mn_major && a->k % 8),
+              "tvt_gemm: contiguous operand extent must be a multiple of 8 elements");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  TVT_REQUIRE(al16(a->a) && al16(a->b) && al16(a->a_lo) && al16(a->b_lo), "tvt_gemm: operands must be 16-byte aligned");
+  TVT_REQUIRE(a->splits >= 1, "tvt_gemm: splits must be >= 1");
+  TVT_REQUIRE(a->splits == 1 || a->atomic_out, "tvt_gemm: split-K requires atomic_out");
+  TVT_REQUIRE(a->out_f32 || a->out_bf16, "tvt_gemm: no output given");
+  if (a->atomic_out) {
+    TVT_REQUIRE(a->out_f32 && !a->out_bf16 && !a->bias && !a->residual && !a->relu_mask && !a->gelu_gate &&
+                    a->act == TVT_ACT_NONE && a->dropout_p == 0.0f && !a->out_preact,
+                "tvt_gemm: atomic_out only supports a plain fp32 accumulate epilogue");
+  }
+  TVT_REQUIRE(a->act >= TVT_ACT_NONE && a->act <= TVT_ACT_GELU, "tvt_gemm: bad act");
+  TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_gemm: dropout_p must be in [0, 1)");
+  TVT_REQUIRE(!a->out_f32 || (a->ld_f32 >= a->n && a->ld_f32 % 4 == 0 && al16(a->out_f32)), "tvt_gemm: bad out_f32 / ld_f32");
+  TVT_REQUIRE(!a->out_bf16 || (a->ld_bf16 >= a->n && a->ld_bf16 % 8 == 0 && al16(a->out_bf16) && al16(a->out_bf16_lo)),
+              "tvt_gemm: bad out_bf16 / ld_bf16");
+  TVT_REQUIRE(!a->out_bf16_lo || a->out_bf16, "tvt_gemm: out_bf16_lo without out_bf16");
+  TVT_REQUIRE(!a->residual || (a->ld_residual >= a->n && a->ld_residual % 8 == 0 && al16(a->residual)), "tvt_gemm: bad residual");
+  TVT_REQUIRE(!a->relu_mask || (a->ld_mask >= a->n && a->ld_mask % 8 == 0 && al16(a->relu_mask)), "tvt_gemm: bad relu_mask");
+  TVT_REQUIRE(!a->gelu_gate || (a->ld_gate >= a->n && a->ld_gate % 8 == 0 && al16(a->gelu_gate)), "tvt_gemm: bad gelu_gate");
+  TVT_REQUIRE(!a->out_preact || (a->ld_preact >= a->n && a->ld_preact % 8 == 0 && al16(a->out_preact)), "tvt_gemm: bad out_preact");
+  TVT_REQUIRE(!a->bias || al16(a->bias), "tvt_gemm: bias must be 16-byte aligned");
+  const long long kb_total = (a->k + gemm::BK - 1) / gemm::BK;
+  TVT_REQUIRE(a->splits <= kb_total, "tvt_gemm: more splits (%d) than k-blocks (%lld)", a->splits, kb_total);
+
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+
+  gemm::Params p{};
+  p.M = (int)a->m; p.N = (int)a->n; p.K = (int)a->k; p.splits = a->splits;
+  p.act = a->act; p.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
+  p.bias = a->bias;
+  p.residual = a->residual; p.residual_f32 = a->residual_dtype == TVT_F32; p.ld_residual = a->ld_residual;
+  p.relu_mask = a->relu_mask; p.mask_f32 = a->mask_dtype == TVT_F32; p.ld_mask = a->ld_mask;
+  p.gelu_gate = a->gelu_gate; p.gate_f32 = a->gate_dtype == TVT_F32; p.ld_gate = a->ld_gate;
+  if (a->dropout_p > 0.0f) {
+    p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
+    p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
+    p.dropout_seed = a->dropout_seed;
+  }
+  p.out_preact = a->out_preact; p.preact_f32 = a->preact_dtype == TVT_F32; p.ld_preact = a->ld_preact;
+  p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32; p.atomic_out = a->atomic_out;
+  p.out_bf16 = (__nv_bfloat16*)a->out_bf16; p.out_bf16_lo = (__nv_bfloat16*)a->out_bf16_lo; p.ld_bf16 = a->ld_bf16;
+
+  p.mn_lbo = gemm::g_mn_lbo; p.mn_sbo = gemm::g_mn_sbo;
+
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // Tile width: 256 columns unless that leaves most SMs idle.
+  const long long tiles256 = ((a->m + 127) / 128) * ((a->n + 255) / 256) * a->splits;
+  const bool narrow = a->n <= 128 || tiles256 < tvt::num_sms();
+  if (a->a_lo) return narrow ? gemm::dispatch_major<128, 2>(a, p, s) : gemm::dispatch_major<256, 2>(a, p, s);
+  return narrow ? gemm::dispatch_major<128, 1>(a, p, s) : gemm::dispatch_major<256, 1>(a, p, s);
+}

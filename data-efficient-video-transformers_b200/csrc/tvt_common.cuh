@@ -1,0 +1,127 @@
+// Shared host/device helpers for the tvt kernels (status handling, vector IO, reductions, RNG).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tvt.h"
+
+namespace tvt {
+
+// ---------------------------------------------------------------- host side
+void set_last_error(const char* fmt, ...);
+int num_sms();
+// Returns TVT_OK or records the CUDA error string and returns TVT_ECUDA.
+int check_launch(const char* what);
+// TVT_EARCH unless the current device is compute capability 10.x.
+int require_sm100();
+
+#define TVT_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::tvt::set_last_error(__VA_ARGS__); \
+      return TVT_EINVAL;                \
+    }                                   \
+  } while (0)
+
+// ---------------------------------------------------------------- device side
+#ifdef __CUDACC__
+
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static __device__ __forceinline__ float to_f(float v) { return v; }
+  static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// 16-byte vector load of kVec elements (8 bf16 / 4 fp32) converted to float.
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int kN = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Exact (erf) GELU and its derivative, matching nn.GELU() default.
+__device__ __forceinline__ float gelu_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Counter-based dropout mask: keep(element) is a pure function of (seed, element index), so the
+// backward pass regenerates the forward mask instead of storing it. One 64-bit mix (splitmix64
+// finaliser) yields 4 independent 16-bit lanes; callers pass idx = element_index / 4.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// 64 random bits covering the 4 consecutive elements [4*elem_div4, 4*elem_div4 + 4).
+__device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t elem_div4) {
+  return mix64(seed ^ (elem_div4 * 0xD6E8FEB86659FD93ull));
+}
+// Lane i (0..3) survives dropout when its 16 random bits are >= thr16 (= p * 65536).
+__device__ __forceinline__ bool dropout_keep_lane(uint64_t bits, int i, uint32_t thr16) {
+  return (static_cast<uint32_t>(bits >> (16 * i)) & 0xFFFFu) >= thr16;
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t elem, uint32_t thr16) {
+  return dropout_keep_lane(dropout_bits4(seed, elem >> 2), static_cast<int>(elem & 3), thr16);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tvt
