@@ -1,0 +1,314 @@
+// LayerNorm forward / backward (see include/tvt.h: tvt_layernorm_fwd / tvt_layernorm_bwd), one warp
+// per token row, the row held in registers (16-byte loads), fp32 statistics via warp shuffles.
+// "Embed" row mapping fuses SimpleTransformer.add_pos_cls (reference src/models/transformer.py:74-82):
+// CLS concat + positional-encoding add + (dropout) + LayerNorm in one pass, and its backward scatter.
+#include "tvt_common.cuh"
+
+namespace tvt {
+namespace ln {
+
+constexpr int kWarps = 8;
+
+struct FwdParams {
+  const void* x;      // [rows, d]  (or, embed mode: frame features [B, T, d])
+  const void* cls;    // embed mode: [B, d] CLS rows, same dtype as x
+  const float* pe;    // embed mode: [S, d] fp32 positional encoding
+  const float* gamma; const float* beta;
+  void* y;            // [rows, d]
+  void* pre;          // embed mode: optional copy of the pre-LN row (x + pe), for backward
+  float* mean; float* rstd;
+  long long rows; int d; int S;  // S > 0 selects embed mode (rows = B * S)
+  float eps;
+  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+};
+
+template <typename T, int kChunks>
+__global__ void __launch_bounds__(kWarps * 32) ln_fwd_kernel(const FwdParams p) {
+  constexpr int V = Vec16<T>::kN;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * kWarps;
+  for (long long row = warp0; row < p.rows; row += nwarps) {
+    const T* src;
+    const float* pe_row = nullptr;
+    if (p.S > 0) {
+      const long long b = row / p.S;
+      const int s = static_cast<int>(row - b * p.S);
+      src = s == 0 ? reinterpret_cast<const T*>(p.cls) + b * p.d
+                   : reinterpret_cast<const T*>(p.x) + (b * (p.S - 1) + (s - 1)) * p.d;
+      pe_row = p.pe + static_cast<long long>(s) * p.d;
+    } else {
+      src = reinterpret_cast<const T*>(p.x) + row * p.d;
+    }
+    float v[kChunks][V];
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      if (col < p.d) {
+        Vec16<T>::load(src + col, v[c]);
+        if (pe_row) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) v[c][i] += pe_row[col + i];
+          if (p.dropout_thr16) {
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+              v[c][i] = dropout_keep(p.dropout_seed, static_cast<unsigned long long>(row) * p.d + col + i, p.dropout_thr16)
+                            ? v[c][i] * p.dropout_scale : 0.0f;
+          }
+          if (p.pre) Vec16<T>::store(reinterpret_cast<T*>(p.pre) + row * p.d + col, v[c]);
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) sum += v[c][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[c][i] = 0.0f;
+      }
+    }
+    const float mean = warp_sum(sum) / p.d;
+    float sq = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      if (col < p.d) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { const float t = v[c][i] - mean; sq += t * t; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / p.d + p.eps);
+    if (lane == 0) {
+      if (p.mean) p.mean[row] = mean;
+      if (p.rstd) p.rstd[row] = rstd;
+    }
+    T* dst = reinterpret_cast<T*>(p.y) + row * p.d;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      if (col < p.d) {
+        float o[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = (v[c][i] - mean) * rstd * __ldg(p.gamma + col + i) + __ldg(p.beta + col + i);
+        Vec16<T>::store(dst + col, o);
+      }
+    }
+  }
+}
+
+struct BwdParams {
+  const void* dy;     // grad wrt LN output [rows, d]
+  const void* x;      // pre-LN input [rows, d]
+  const float* mean; const float* rstd; const float* gamma;
+  void* dx;           // grad wrt pre-LN input [rows, d]            (nullable in embed mode)
+  void* dz;           // optional: dropout-masked copy of dx (the branch gradient) [rows, d]
+  void* dfeat;        // embed mode: grad wrt frame features [B, T, d]
+  void* dcls;         // embed mode: grad wrt CLS rows [B, d]
+  float* dgamma; float* dbeta;  // [d], accumulated with atomics (caller zero-fills)
+  float* dbias;       // optional [d]: column sum of dz (or dx when dz is null)
+  long long rows; int d; int S;
+  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+  long long dropout_ld;  // row pitch used for dropout element indices (N of the producing GEMM)
+};
+
+template <typename T, int kChunks>
+__global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const BwdParams p) {
+  constexpr int V = Vec16<T>::kN;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kWarps + warp;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kWarps;
+  float acc_g[kChunks][V], acc_b[kChunks][V], acc_z[kChunks][V];
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc_g[c][i] = acc_b[c][i] = acc_z[c][i] = 0.0f;
+
+  for (long long row = warp0; row < p.rows; row += nwarps) {
+    const T* dy = reinterpret_cast<const T*>(p.dy) + row * p.d;
+    const T* x = reinterpret_cast<const T*>(p.x) + row * p.d;
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    float g[kChunks][V], xh[kChunks][V];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      if (col < p.d) {
+        float dyv[V], xv[V];
+        Vec16<T>::load(dy + col, dyv);
+        Vec16<T>::load(x + col, xv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          xh[c][i] = (xv[i] - mean) * rstd;
+          acc_g[c][i] += dyv[i] * xh[c][i];
+          acc_b[c][i] += dyv[i];
+          g[c][i] = dyv[i] * __ldg(p.gamma + col + i);
+          s1 += g[c][i];
+          s2 += g[c][i] * xh[c][i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[c][i] = xh[c][i] = 0.0f;
+      }
+    }
+    s1 = warp_sum(s1) / p.d;
+    s2 = warp_sum(s2) / p.d;
+    // destination rows (embed mode scatters to the feature / CLS gradients)
+    T* dx_row = p.dx ? reinterpret_cast<T*>(p.dx) + row * p.d : nullptr;
+    T* dz_row = p.dz ? reinterpret_cast<T*>(p.dz) + row * p.d : nullptr;
+    if (p.S > 0) {
+      const long long b = row / p.S;
+      const int s = static_cast<int>(row - b * p.S);
+      dz_row = s == 0 ? (p.dcls ? reinterpret_cast<T*>(p.dcls) + b * p.d : nullptr)
+                      : (p.dfeat ? reinterpret_cast<T*>(p.dfeat) + (b * (p.S - 1) + (s - 1)) * p.d : nullptr);
+    }
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      if (col < p.d) {
+        float o[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+        if (dx_row) Vec16<T>::store(dx_row + col, o);
+        if (p.dropout_thr16) {
+#pragma unroll
+          for (int i = 0; i < V; ++i)
+            o[i] = dropout_keep(p.dropout_seed, static_cast<unsigned long long>(row) * p.dropout_ld + col + i, p.dropout_thr16)
+                       ? o[i] * p.dropout_scale : 0.0f;
+        }
+        if (dz_row) Vec16<T>::store(dz_row + col, o);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc_z[c][i] += o[i];
+      }
+    }
+  }
+  // CTA-level reduction of the column partials through shared memory, then one atomic per column.
+  __shared__ float red[kWarps][32 * V + 1];
+  for (int which = 0; which < 3; ++which) {
+    float* out = which == 0 ? p.dgamma : (which == 1 ? p.dbeta : p.dbias);
+    if (!out) continue;  // uniform
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        red[warp][lane * V + i] = which == 0 ? acc_g[c][i] : (which == 1 ? acc_b[c][i] : acc_z[c][i]);
+      __syncthreads();
+      for (int t = threadIdx.x; t < 32 * V; t += kWarps * 32) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += red[w][t];
+        const int col = c * 32 * V + t;
+        if (col < p.d) atomicAdd(out + col, s);
+      }
+    }
+  }
+}
+
+template <typename T, template <typename, int> class Launcher, typename P>
+static int dispatch_chunks(const P& p, int d, cudaStream_t s) {
+  constexpr int V = Vec16<T>::kN;
+  const int chunks = (d + 32 * V - 1) / (32 * V);
+  if (chunks <= 1) return Launcher<T, 1>::run(p, s);
+  if (chunks <= 2) return Launcher<T, 2>::run(p, s);
+  if (chunks <= 3) return Launcher<T, 3>::run(p, s);
+  if (chunks <= 4) return Launcher<T, 4>::run(p, s);
+  if (chunks <= 6) return Launcher<T, 6>::run(p, s);
+  if (chunks <= 8) return Launcher<T, 8>::run(p, s);
+  if (chunks <= 16) return Launcher<T, 16>::run(p, s);
+  set_last_error("layernorm: d=%d too wide (max %d)", d, 16 * 32 * V);
+  return TVT_EINVAL;
+}
+
+static int grid_for(long long rows) {
+  const long long want = (rows + kWarps - 1) / kWarps;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <typename T, int C>
+struct FwdLauncher {
+  static int run(const FwdParams& p, cudaStream_t s) {
+    ln_fwd_kernel<T, C><<<grid_for(p.rows), kWarps * 32, 0, s>>>(p);
+    return check_launch("tvt_layernorm_fwd");
+  }
+};
+template <typename T, int C>
+struct BwdLauncher {
+  static int run(const BwdParams& p, cudaStream_t s) {
+    // fewer, fatter CTAs: each ends with d atomics per output vector
+    const long long want = (p.rows + kWarps * 4 - 1) / (kWarps * 4);
+    const long long cap = static_cast<long long>(num_sms()) * 2;
+    const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+    ln_bwd_kernel<T, C><<<grid, kWarps * 32, 0, s>>>(p);
+    return check_launch("tvt_layernorm_bwd");
+  }
+};
+
+}  // namespace ln
+}  // namespace tvt
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr, "tvt_layernorm_fwd: null args");
+  TVT_REQUIRE(a->x && a->y && a->gamma && a->beta, "tvt_layernorm_fwd: null pointer");
+  TVT_REQUIRE(a->rows >= 0 && a->d > 0 && a->d % 8 == 0, "tvt_layernorm_fwd: d must be a positive multiple of 8 (got %lld)", (long long)a->d);
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_layernorm_fwd: bad dtype");
+  TVT_REQUIRE(al16(a->x) && al16(a->y) && al16(a->cls) && al16(a->pre), "tvt_layernorm_fwd: pointers must be 16-byte aligned");
+  TVT_REQUIRE(a->seq_len >= 0, "tvt_layernorm_fwd: bad seq_len");
+  if (a->seq_len > 0) {
+    TVT_REQUIRE(a->cls && a->pe, "tvt_layernorm_fwd: embed mode needs cls and pe");
+    TVT_REQUIRE(a->seq_len >= 2 && a->rows % a->seq_len == 0, "tvt_layernorm_fwd: rows must be a multiple of seq_len");
+  }
+  TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_layernorm_fwd: dropout_p must be in [0,1)");
+  TVT_REQUIRE(a->dropout_p == 0.0f || a->seq_len > 0, "tvt_layernorm_fwd: dropout only applies in embed mode");
+  if (a->rows == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  ln::FwdParams p{};
+  p.x = a->x; p.cls = a->cls; p.pe = a->pe; p.gamma = a->gamma; p.beta = a->beta; p.y = a->y; p.pre = a->pre;
+  p.mean = a->mean; p.rstd = a->rstd; p.rows = a->rows; p.d = (int)a->d; p.S = (int)a->seq_len; p.eps = a->eps;
+  if (a->dropout_p > 0.0f) {
+    p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
+    p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
+    p.dropout_seed = a->dropout_seed;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::FwdLauncher>(p, p.d, s)
+                             : ln::dispatch_chunks<__nv_bfloat16, ln::FwdLauncher>(p, p.d, s);
+}
+
+extern "C" int tvt_layernorm_bwd(const tvt_layernorm_bwd_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr, "tvt_layernorm_bwd: null args");
+  TVT_REQUIRE(a->dy && a->x && a->mean && a->rstd && a->gamma, "tvt_layernorm_bwd: null pointer");
+  TVT_REQUIRE(a->rows >= 0 && a->d > 0 && a->d % 8 == 0, "tvt_layernorm_bwd: d must be a positive multiple of 8");
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_layernorm_bwd: bad dtype");
+  TVT_REQUIRE(al16(a->dy) && al16(a->x) && al16(a->dx) && al16(a->dz) && al16(a->dfeat) && al16(a->dcls),
+              "tvt_layernorm_bwd: pointers must be 16-byte aligned");
+  if (a->seq_len > 0) {
+    TVT_REQUIRE(a->seq_len >= 2 && a->rows % a->seq_len == 0, "tvt_layernorm_bwd: rows must be a multiple of seq_len");
+    TVT_REQUIRE(!a->dz, "tvt_layernorm_bwd: dz is implied by dfeat/dcls in embed mode");
+  } else {
+    TVT_REQUIRE(a->dx, "tvt_layernorm_bwd: dx required");
+    TVT_REQUIRE(!a->dfeat && !a->dcls, "tvt_layernorm_bwd: dfeat/dcls need seq_len > 0");
+  }
+  TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_layernorm_bwd: dropout_p must be in [0,1)");
+  if (a->rows == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  ln::BwdParams p{};
+  p.dy = a->dy; p.x = a->x; p.mean = a->mean; p.rstd = a->rstd; p.gamma = a->gamma;
+  p.dx = a->dx; p.dz = a->dz; p.dfeat = a->dfeat; p.dcls = a->dcls;
+  p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
+  p.rows = a->rows; p.d = (int)a->d; p.S = (int)a->seq_len;
+  if (a->dropout_p > 0.0f) {
+    p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
+    p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
+    p.dropout_seed = a->dropout_seed;
+  }
+  p.dropout_ld = a->d;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::BwdLauncher>(p, p.d, s)
+                             : ln::dispatch_chunks<__nv_bfloat16, ln::BwdLauncher>(p, p.d, s);
+}

@@ -1,0 +1,356 @@
+// Small bandwidth / latency kernels on the hot path (see include/tvt.h): column sums for bias
+// gradients, fp32 -> bf16 (hi, lo) splitting, bias+activation after split-K GEMMs, the skinny class-head
+// linear layer and the CLS gather + expert sum of SimpleTransformer.ptn (src/models/transformer.py:123-130).
+#include "tvt_common.cuh"
+
+namespace tvt {
+namespace misc {
+
+// ---------------------------------------------------------------- colsum
+// grid (col tiles of 32*V, row slabs); each thread owns V columns and strides over the rows of its slab.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* x, float* out, long long rows, long long cols, long long ld, long long rows_per_slab) {
+  constexpr int V = Vec16<T>::kN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long col = (blockIdx.x * 32ll + lane) * V;
+  const long long r0 = blockIdx.y * rows_per_slab, r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.0f;
+  if (col < cols) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      float v[V];
+      Vec16<T>::load(x + r * ld + col, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += v[i];
+    }
+  }
+  __shared__ float red[8][32 * V + 1];
+#pragma unroll
+  for (int i = 0; i < V; ++i) red[warp][lane * V + i] = acc[i];
+  __syncthreads();
+  for (int t = threadIdx.x; t < 32 * V; t += 256) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][t];
+    const long long c = blockIdx.x * 32ll * V + t;
+    if (c < cols) atomicAdd(out + c, s);
+  }
+}
+
+// ---------------------------------------------------------------- split
+__global__ void __launch_bounds__(256) split_kernel(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8], h[8], l[8];
+      const float4 a = *reinterpret_cast<const float4*>(x + i), b = *reinterpret_cast<const float4*>(x + i + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = __bfloat162float(__float2bfloat16_rn(v[j])); l[j] = v[j] - h[j]; }
+      Vec16<__nv_bfloat16>::store(hi + i, h);
+      if (lo) Vec16<__nv_bfloat16>::store(lo + i, l);
+    } else {
+      for (long long j = i; j < n; ++j) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(x[j]);
+        hi[j] = h;
+        if (lo) lo[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- bias + act (+dropout)
+template <typename T>
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* x, const float* bias, T* y, long long rows, long long cols, int act,
+                                                       float dscale, unsigned thr16, unsigned long long seed) {
+  const long long n = rows * cols;
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i);
+    float v[4] = {a.x, a.y, a.z, a.w};
+    const long long c = i % cols;
+    const uint64_t bits = thr16 ? dropout_bits4(seed, static_cast<unsigned long long>(i) >> 2) : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (bias) v[j] += bias[c + j];
+      if (act == TVT_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
+      else if (act == TVT_ACT_GELU) v[j] = gelu_f(v[j]);
+      if (thr16) v[j] = dropout_keep_lane(bits, j, thr16) ? v[j] * dscale : 0.0f;
+      y[i + j] = Elem<T>::from_f(v[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- positional encoding
+template <typename T>
+__global__ void __launch_bounds__(256) posenc_kernel(const T* x, const float* pe, T* y, long long rows, int d, int S, float dscale,
+                                                     unsigned thr16, unsigned long long seed) {
+  constexpr int V = Vec16<T>::kN;
+  const long long n = rows * d;
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * V; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * V) {
+    const long long row = i / d;
+    const int col = static_cast<int>(i - row * d);
+    const float* pr = pe + (row % S) * d + col;
+    float v[V];
+    Vec16<T>::load(x + i, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j] += pr[j];
+      if (thr16) v[j] = dropout_keep(seed, static_cast<unsigned long long>(i + j), thr16) ? v[j] * dscale : 0.0f;
+    }
+    Vec16<T>::store(y + i, v);
+  }
+}
+
+// ---------------------------------------------------------------- activation backward
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* dy, const T* yz, T* dx, long long n, int act, float dscale, unsigned thr16,
+                                                      unsigned long long seed) {
+  constexpr int V = Vec16<T>::kN;
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * V; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * V) {
+    float g[V], r[V];
+    Vec16<T>::load(dy + i, g);
+    Vec16<T>::load(yz + i, r);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if (act == TVT_ACT_RELU) g[j] = r[j] > 0.0f ? g[j] : 0.0f;
+      else if (act == TVT_ACT_GELU) g[j] *= gelu_grad_f(r[j]);
+      if (thr16) g[j] = dropout_keep(seed, static_cast<unsigned long long>(i + j), thr16) ? g[j] * dscale : 0.0f;
+    }
+    Vec16<T>::store(dx + i, g);
+  }
+}
+
+// ---------------------------------------------------------------- class-head linear
+template <typename T>
+__global__ void __launch_bounds__(128) head_fwd_kernel(const T* x, const float* w, const float* b, float* y, long long M, long long K, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long m = blockIdx.x * 4ll + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const T* xr = x + m * K;
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.0f;
+    for (long long k = lane; k < K; k += 32) acc += Elem<T>::to_f(xr[k]) * __ldg(w + c * K + k);
+    acc = warp_sum(acc);
+    if (lane == 0) y[m * C + c] = acc + (b ? b[c] : 0.0f);
+  }
+}
+// dx[m,k] = sum_c dy[m,c] w[c,k]
+template <typename T>
+__global__ void __launch_bounds__(256) head_dx_kernel(const float* dy, const float* w, T* dx, long long M, long long K, int C) {
+  const long long n = M * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / K, k = i - m * K;
+    float acc = 0.0f;
+    for (int c = 0; c < C; ++c) acc += dy[m * C + c] * __ldg(w + c * K + k);
+    dx[i] = Elem<T>::from_f(acc);
+  }
+}
+// dw[c,k] += sum_m dy[m,c] x[m,k];  db[c] += sum_m dy[m,c]   (one owner thread per (c,k): no atomics)
+template <typename T>
+__global__ void __launch_bounds__(256) head_dw_kernel(const float* dy, const T* x, float* dw, float* db, long long M, long long K, int C) {
+  const long long n = static_cast<long long>(C) * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long c = i / K, k = i - c * K;
+    float acc = 0.0f, accb = 0.0f;
+    for (long long m = 0; m < M; ++m) {
+      const float g = dy[m * C + c];
+      acc += g * Elem<T>::to_f(x[m * K + k]);
+      accb += g;
+    }
+    dw[i] += acc;
+    if (k == 0 && db) db[c] += accb;
+  }
+}
+
+// ---------------------------------------------------------------- CLS gather + expert sum
+struct ClsParams { const void* tok[TVT_MAX_EXPERTS]; void* out; long long B, S, d; int E; };
+template <typename T>
+__global__ void __launch_bounds__(256) cls_sum_kernel(const ClsParams p) {
+  constexpr int V = Vec16<T>::kN;
+  const long long vecs = p.d / V, n = p.B * vecs;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / vecs;
+    const int col = static_cast<int>(i - b * vecs) * V;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+    for (int e = 0; e < p.E; ++e) {
+      float v[V];
+      Vec16<T>::load(reinterpret_cast<const T*>(p.tok[e]) + b * p.S * p.d + col, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += v[j];
+    }
+    Vec16<T>::store(reinterpret_cast<T*>(p.out) + b * p.d + col, acc);
+  }
+}
+
+static int grid1d(long long items, int threads) {
+  const long long want = (items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+}  // namespace misc
+}  // namespace tvt
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int tvt_colsum(const tvt_colsum_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->x && a->out, "tvt_colsum: null pointer");
+  TVT_REQUIRE(a->rows >= 0 && a->cols > 0 && a->cols % 8 == 0 && a->ld >= a->cols && a->ld % 8 == 0, "tvt_colsum: cols and ld must be multiples of 8");
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_colsum: bad dtype");
+  TVT_REQUIRE(al16(a->x), "tvt_colsum: x must be 16-byte aligned");
+  if (a->rows == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  const int V = a->dtype == TVT_F32 ? 4 : 8;
+  const long long col_tiles = (a->cols + 32 * V - 1) / (32 * V);
+  long long slabs = (static_cast<long long>(num_sms()) * 4 + col_tiles - 1) / col_tiles;
+  const long long max_slabs = (a->rows + 63) / 64;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  const long long rps = (a->rows + slabs - 1) / slabs;
+  dim3 grid(static_cast<unsigned>(col_tiles), static_cast<unsigned>((a->rows + rps - 1) / rps));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->dtype == TVT_F32) misc::colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)a->x, a->out, a->rows, a->cols, a->ld, rps);
+  else misc::colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a->x, a->out, a->rows, a->cols, a->ld, rps);
+  return check_launch("tvt_colsum");
+}
+
+extern "C" int tvt_split_f32(const tvt_split_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->x && a->hi, "tvt_split_f32: null pointer");
+  TVT_REQUIRE(a->n >= 0, "tvt_split_f32: negative size");
+  TVT_REQUIRE(al16(a->x) && al16(a->hi) && al16(a->lo), "tvt_split_f32: pointers must be 16-byte aligned");
+  if (a->n == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  misc::split_kernel<<<misc::grid1d((a->n + 7) / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a->x, (__nv_bfloat16*)a->hi, (__nv_bfloat16*)a->lo, a->n);
+  return check_launch("tvt_split_f32");
+}
+
+extern "C" int tvt_bias_act_fwd(const tvt_bias_act_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->x && a->y, "tvt_bias_act_fwd: null pointer");
+  TVT_REQUIRE(a->rows >= 0 && a->cols > 0 && a->cols % 4 == 0, "tvt_bias_act_fwd: cols must be a multiple of 4");
+  TVT_REQUIRE(a->out_dtype == TVT_BF16 || a->out_dtype == TVT_F32, "tvt_bias_act_fwd: bad dtype");
+  TVT_REQUIRE(a->act >= TVT_ACT_NONE && a->act <= TVT_ACT_GELU, "tvt_bias_act_fwd: bad act");
+  TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_bias_act_fwd: dropout_p must be in [0,1)");
+  TVT_REQUIRE(al16(a->x), "tvt_bias_act_fwd: x must be 16-byte aligned");
+  if (a->rows == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  unsigned thr = 0; float sc = 1.0f;
+  if (a->dropout_p > 0.0f) { thr = (unsigned)(a->dropout_p * 65536.0f + 0.5f); sc = 65536.0f / (65536.0f - (float)thr); }
+  const long long n4 = a->rows * a->cols / 4;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->out_dtype == TVT_F32) misc::bias_act_kernel<float><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (float*)a->y, a->rows, a->cols, a->act, sc, thr, a->dropout_seed);
+  else misc::bias_act_kernel<__nv_bfloat16><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (__nv_bfloat16*)a->y, a->rows, a->cols, a->act, sc, thr, a->dropout_seed);
+  return check_launch("tvt_bias_act_fwd");
+}
+
+extern "C" int tvt_posenc_fwd(const tvt_posenc_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->x && a->pe && a->y, "tvt_posenc_fwd: null pointer");
+  TVT_REQUIRE(a->rows >= 0 && a->d > 0 && a->d % 8 == 0 && a->seq_len > 0, "tvt_posenc_fwd: bad shape (d must be a multiple of 8)");
+  TVT_REQUIRE(a->rows % a->seq_len == 0, "tvt_posenc_fwd: rows must be a multiple of seq_len");
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_posenc_fwd: bad dtype");
+  TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_posenc_fwd: dropout_p must be in [0,1)");
+  TVT_REQUIRE(al16(a->x) && al16(a->y), "tvt_posenc_fwd: pointers must be 16-byte aligned");
+  if (a->rows == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  unsigned thr = 0; float sc = 1.0f;
+  if (a->dropout_p > 0.0f) { thr = (unsigned)(a->dropout_p * 65536.0f + 0.5f); sc = 65536.0f / (65536.0f - (float)thr); }
+  const long long n = a->rows * a->d;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->dtype == TVT_F32) misc::posenc_kernel<float><<<misc::grid1d(n / 4, 256), 256, 0, s>>>((const float*)a->x, a->pe, (float*)a->y, a->rows, (int)a->d, (int)a->seq_len, sc, thr, a->dropout_seed);
+  else misc::posenc_kernel<__nv_bfloat16><<<misc::grid1d(n / 8, 256), 256, 0, s>>>((const __nv_bfloat16*)a->x, a->pe, (__nv_bfloat16*)a->y, a->rows, (int)a->d, (int)a->seq_len, sc, thr, a->dropout_seed);
+  return check_launch("tvt_posenc_fwd");
+}
+
+extern "C" int tvt_act_bwd(const tvt_act_bwd_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->dy && a->y_or_z && a->dx, "tvt_act_bwd: null pointer");
+  TVT_REQUIRE(a->rows >= 0 && a->cols > 0 && (a->rows * a->cols) % 8 == 0, "tvt_act_bwd: element count must be a multiple of 8");
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_act_bwd: bad dtype");
+  TVT_REQUIRE(a->act >= TVT_ACT_NONE && a->act <= TVT_ACT_GELU, "tvt_act_bwd: bad act");
+  TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_act_bwd: dropout_p must be in [0,1)");
+  TVT_REQUIRE(al16(a->dy) && al16(a->y_or_z) && al16(a->dx), "tvt_act_bwd: pointers must be 16-byte aligned");
+  if (a->rows == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  unsigned thr = 0; float sc = 1.0f;
+  if (a->dropout_p > 0.0f) { thr = (unsigned)(a->dropout_p * 65536.0f + 0.5f); sc = 65536.0f / (65536.0f - (float)thr); }
+  const long long n = a->rows * a->cols;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->dtype == TVT_F32) misc::act_bwd_kernel<float><<<misc::grid1d(n / 4, 256), 256, 0, s>>>((const float*)a->dy, (const float*)a->y_or_z, (float*)a->dx, n, a->act, sc, thr, a->dropout_seed);
+  else misc::act_bwd_kernel<__nv_bfloat16><<<misc::grid1d(n / 8, 256), 256, 0, s>>>((const __nv_bfloat16*)a->dy, (const __nv_bfloat16*)a->y_or_z, (__nv_bfloat16*)a->dx, n, a->act, sc, thr, a->dropout_seed);
+  return check_launch("tvt_act_bwd");
+}
+
+extern "C" int tvt_head_linear_fwd(const tvt_head_linear_fwd_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->x && a->w && a->y, "tvt_head_linear_fwd: null pointer");
+  TVT_REQUIRE(a->m > 0 && a->k > 0 && a->classes > 0 && a->classes <= 1024, "tvt_head_linear_fwd: bad shape");
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_head_linear_fwd: bad dtype");
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  const int grid = static_cast<int>((a->m + 3) / 4);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->dtype == TVT_F32) misc::head_fwd_kernel<float><<<grid, 128, 0, s>>>((const float*)a->x, a->w, a->b, a->y, a->m, a->k, (int)a->classes);
+  else misc::head_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>((const __nv_bfloat16*)a->x, a->w, a->b, a->y, a->m, a->k, (int)a->classes);
+  return check_launch("tvt_head_linear_fwd");
+}
+
+extern "C" int tvt_head_linear_bwd(const tvt_head_linear_bwd_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->dy && a->w && a->x, "tvt_head_linear_bwd: null pointer");
+  TVT_REQUIRE(a->m > 0 && a->k > 0 && a->classes > 0 && a->classes <= 1024, "tvt_head_linear_bwd: bad shape");
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_head_linear_bwd: bad dtype");
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int C = (int)a->classes;
+  if (a->dx) {
+    const int g = misc::grid1d(a->m * a->k, 256);
+    if (a->dtype == TVT_F32) misc::head_dx_kernel<float><<<g, 256, 0, s>>>(a->dy, a->w, (float*)a->dx, a->m, a->k, C);
+    else misc::head_dx_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(a->dy, a->w, (__nv_bfloat16*)a->dx, a->m, a->k, C);
+    rc = check_launch("tvt_head_linear_bwd(dx)");
+    if (rc != TVT_OK) return rc;
+  }
+  if (a->dw) {
+    const int g = misc::grid1d(a->classes * a->k, 256);
+    if (a->dtype == TVT_F32) misc::head_dw_kernel<float><<<g, 256, 0, s>>>(a->dy, (const float*)a->x, a->dw, a->db, a->m, a->k, C);
+    else misc::head_dw_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(a->dy, (const __nv_bfloat16*)a->x, a->dw, a->db, a->m, a->k, C);
+    rc = check_launch("tvt_head_linear_bwd(dw)");
+  }
+  return rc;
+}
+
+extern "C" int tvt_cls_sum_fwd(const tvt_cls_sum_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->out, "tvt_cls_sum_fwd: null pointer");
+  TVT_REQUIRE(a->num_experts >= 1 && a->num_experts <= TVT_MAX_EXPERTS, "tvt_cls_sum_fwd: num_experts out of range");
+  TVT_REQUIRE(a->batch > 0 && a->seq_len > 0 && a->d > 0 && a->d % 8 == 0, "tvt_cls_sum_fwd: bad shape");
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_cls_sum_fwd: bad dtype");
+  misc::ClsParams p{};
+  for (int e = 0; e < a->num_experts; ++e) {
+    TVT_REQUIRE(a->tokens[e] && al16(a->tokens[e]), "tvt_cls_sum_fwd: bad token pointer");
+    p.tok[e] = a->tokens[e];
+  }
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  p.out = a->out; p.B = a->batch; p.S = a->seq_len; p.d = a->d; p.E = a->num_experts;
+  const long long items = a->batch * (a->d / (a->dtype == TVT_F32 ? 4 : 8));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->dtype == TVT_F32) misc::cls_sum_kernel<float><<<misc::grid1d(items, 256), 256, 0, s>>>(p);
+  else misc::cls_sum_kernel<__nv_bfloat16><<<misc::grid1d(items, 256), 256, 0, s>>>(p);
+  return check_launch("tvt_cls_sum_fwd");
+}

@@ -1,0 +1,7 @@
+"""Host-side mirror of the reference's model API (src/models/*.py): same class names, constructor
+arguments, forward signatures, Lightning hook names and state_dict keys; the arithmetic underneath runs
+on the package's sm_100a kernels through torch.autograd.Functions (see ..functions)."""
+from .transformer import PositionalEncoding, SimpleTransformer  # noqa: F401
+from .frame_transformer import TransformerBase, FrameStream  # noqa: F401
+from .TPN import Reasoning, sum_group, SpatialPyramid  # noqa: F401
+from .fusion import CrossModalBlock, ExpertStream, FusionTransformer, DistillationTrainer  # noqa: F401

@@ -1,0 +1,383 @@
+"""Functional layer over the C-ABI: every function takes/returns torch CUDA tensors and launches
+hand-written sm_100a kernels from libtvt_b200.so on torch's current stream.  No function here has a
+PyTorch/CPU fallback: a missing library or a non-CUDA tensor raises.
+
+Precision modes (``Mode``):
+  "bf16": activations and GEMM operands bf16, fp32 accumulation / statistics / losses, fp32 master weights.
+  "fp32": activations fp32; every GEMM operand is split into two bf16 planes (hi + lo) and the tensor
+          cores run hi*hi + hi*lo + lo*hi — the "fp32-accumulate" parity mode (1e-3 tolerance).
+"""
+import weakref
+
+import torch
+
+from . import capi
+from .capi import ACT_GELU, ACT_NONE, ACT_RELU, TVT_BF16, TVT_F32, TvtError
+
+_NUM_SMS = None
+
+
+def num_sms():
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _NUM_SMS
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return TVT_F32
+    if t.dtype == torch.bfloat16:
+        return TVT_BF16
+    raise TvtError(f"unsupported dtype {t.dtype}: the kernels take bf16 or fp32")
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise TvtError("tensor is not on a CUDA device: this path has no CPU implementation")
+
+
+def _rowmajor(t):
+    if t.stride(-1) != 1:
+        raise TvtError("innermost dimension must be contiguous")
+    return t.stride(0)
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm(a, b, m, n, k, *, a_lo=None, b_lo=None, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None,
+         act=ACT_NONE, alpha=1.0, residual=None, relu_mask=None, gelu_gate=None, dropout_p=0.0, seed=0,
+         out_f32=None, out_bf16=None, out_bf16_lo=None, out_preact=None, splits=1, atomic=False):
+    _cuda(a, b, a_lo, b_lo, bias, residual, relu_mask, gelu_gate, out_f32, out_bf16, out_bf16_lo, out_preact)
+    g = capi.GemmArgs()
+    g.a, g.a_lo, g.b, g.b_lo = _p(a), _p(a_lo), _p(b), _p(b_lo)
+    g.m, g.n, g.k = m, n, k
+    g.lda = lda if lda is not None else _rowmajor(a)
+    g.ldb = ldb if ldb is not None else _rowmajor(b)
+    g.a_mn_major, g.b_mn_major, g.splits, g.act, g.alpha = int(a_mn), int(b_mn), splits, act, alpha
+    g.bias = _p(bias)
+    if residual is not None:
+        g.residual, g.residual_dtype, g.ld_residual = _p(residual), _dt(residual), _rowmajor(residual)
+    if relu_mask is not None:
+        g.relu_mask, g.mask_dtype, g.ld_mask = _p(relu_mask), _dt(relu_mask), _rowmajor(relu_mask)
+    if gelu_gate is not None:
+        g.gelu_gate, g.gate_dtype, g.ld_gate = _p(gelu_gate), _dt(gelu_gate), _rowmajor(gelu_gate)
+    g.dropout_p, g.dropout_seed = dropout_p, seed
+    if out_preact is not None:
+        g.out_preact, g.preact_dtype, g.ld_preact = _p(out_preact), _dt(out_preact), _rowmajor(out_preact)
+    if out_f32 is not None:
+        g.out_f32, g.ld_f32 = _p(out_f32), _rowmajor(out_f32)
+    g.atomic_out = int(atomic)
+    if out_bf16 is not None:
+        g.out_bf16, g.out_bf16_lo, g.ld_bf16 = _p(out_bf16), _p(out_bf16_lo), _rowmajor(out_bf16)
+    capi.call("tvt_gemm", g, _stream())
+
+
+def split_f32(x, hi, lo=None):
+    _cuda(x, hi, lo)
+    s = capi.SplitArgs(_p(x), _p(hi), _p(lo), x.numel())
+    capi.call("tvt_split_f32", s, _stream())
+
+
+def colsum(x, out):
+    """out[c] += sum_r x[r, c]; out fp32, zero-filled by the caller."""
+    _cuda(x, out)
+    a = capi.ColsumArgs(_p(x), _p(out), x.shape[0], x.shape[1], _rowmajor(x), _dt(x))
+    capi.call("tvt_colsum", a, _stream())
+
+
+def bias_act(x, bias, out, act=ACT_NONE, dropout_p=0.0, seed=0):
+    _cuda(x, bias, out)
+    a = capi.BiasActArgs(_p(x), _p(bias), _p(out), x.shape[0], x.shape[1], _dt(out), act, dropout_p, seed)
+    capi.call("tvt_bias_act_fwd", a, _stream())
+
+
+def posenc_fwd(x, pe, S, dropout_p=0.0, seed=0):
+    """x [B*S, d] batch-major tokens, pe fp32 [S, d] -> dropout(x + pe[s])."""
+    _cuda(x, pe)
+    y = torch.empty_like(x)
+    a = capi.PosencArgs(_p(x), _p(pe), _p(y), x.shape[0], x.shape[1], S, _dt(x), dropout_p, seed)
+    capi.call("tvt_posenc_fwd", a, _stream())
+    return y
+
+
+def act_bwd(dy, y_or_z, act, dropout_p=0.0, seed=0):
+    _cuda(dy, y_or_z)
+    dx = torch.empty_like(dy)
+    a = capi.ActBwdArgs(_p(dy), _p(y_or_z), _p(dx), dy.shape[0], dy.shape[1], _dt(dy), act, dropout_p, seed)
+    capi.call("tvt_act_bwd", a, _stream())
+    return dx
+
+
+class Mode:
+    """Precision mode + per-step cache of bf16 weight planes (keyed on the parameter's version counter)."""
+
+    def __init__(self, name="bf16"):
+        if name not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {name!r}")
+        self.name = name
+        self.fp32 = name == "fp32"
+        self.dtype = torch.float32 if self.fp32 else torch.bfloat16
+        self.tvt = TVT_F32 if self.fp32 else TVT_BF16
+        self._wcache = {}
+
+    def split(self, x):
+        """Activation [rows, cols] -> (hi, lo) bf16 GEMM operand planes."""
+        if not self.fp32:
+            if x.dtype != torch.bfloat16:
+                raise TvtError("bf16 mode expects bf16 activations")
+            return x, None
+        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
+        split_f32(x.contiguous(), hi, lo)
+        return hi, lo
+
+    def weight(self, w, rows=None):
+        """fp32 master weight [N, K] -> cached (hi, lo) bf16 planes, refreshed when the parameter changes
+        (version counter) — one conversion per optimizer step.  ``rows=(r0, r1)`` selects a row slice
+        (e.g. the q / kv parts of a packed in_proj_weight)."""
+        ent = self._wcache.get(id(w))
+        if ent is None or ent[0]() is not w or ent[1] != w._version:
+            wd = w.detach()
+            if wd.dtype != torch.float32:
+                raise TvtError("master weights must be fp32")
+            hi = torch.empty(wd.shape, dtype=torch.bfloat16, device=wd.device)
+            lo = torch.empty_like(hi) if self.fp32 else None
+            split_f32(wd.contiguous(), hi, lo)
+            ent = (weakref.ref(w), w._version, hi, lo)
+            self._wcache[id(w)] = ent
+        hi, lo = ent[2], ent[3]
+        if rows is not None:
+            hi = hi[rows[0]:rows[1]]
+            lo = lo[rows[0]:rows[1]] if lo is not None else None
+        return hi, lo
+
+    def empty(self, *shape, device):
+        return torch.empty(*shape, dtype=self.dtype, device=device)
+
+    # y[M,N] = act(x W^T + b) (+dropout) (+residual)
+    def linear_fwd(self, xp, M, K, W, b, *, act=ACT_NONE, residual=None, dropout_p=0.0, seed=0, preact=None,
+                   rows=None):
+        wh, wl = self.weight(W, rows)
+        N = wh.shape[0]
+        y = self.empty(M, N, device=xp[0].device)
+        gemm(xp[0], wh, M, N, K, a_lo=xp[1], b_lo=wl, lda=_rowmajor(xp[0]), ldb=K, bias=b, act=act,
+             residual=residual, dropout_p=dropout_p, seed=seed, out_preact=preact,
+             out_f32=y if self.fp32 else None, out_bf16=None if self.fp32 else y)
+        return y
+
+    # dx[M,K] = dy[M,N] W[N,K]  (* relu mask, * gelu', dropout, + residual)
+    def dgrad(self, dyp, M, N, W, *, residual=None, relu_mask=None, gelu_gate=None, dropout_p=0.0, seed=0,
+              rows=None):
+        K = W.shape[1]
+        wh, wl = self.weight(W, rows)
+        dx = self.empty(M, K, device=dyp[0].device)
+        gemm(dyp[0], wh, M, K, N, a_lo=dyp[1], b_lo=wl, lda=_rowmajor(dyp[0]), ldb=_rowmajor(wh), b_mn=True,
+             residual=residual, relu_mask=relu_mask, gelu_gate=gelu_gate, dropout_p=dropout_p, seed=seed,
+             out_f32=dx if self.fp32 else None, out_bf16=None if self.fp32 else dx)
+        return dx
+
+    # dW[N,K] = dy[M,N]^T x[M,K]  (fp32, split-K over the token dimension when the tile grid is small)
+    def wgrad(self, dyp, xp, M, N, K, out=None):
+        tiles = ((N + 127) // 128) * ((K + 255) // 256)
+        kb = (M + 63) // 64
+        splits = max(1, min(kb, num_sms() // max(tiles, 1)))
+        if out is None:
+            out = (torch.zeros if splits > 1 else torch.empty)(N, K, dtype=torch.float32, device=dyp[0].device)
+        elif splits > 1:
+            out.zero_()
+        gemm(dyp[0], xp[0], N, K, M, a_lo=dyp[1], b_lo=xp[1], a_mn=True, b_mn=True, lda=_rowmajor(dyp[0]),
+             ldb=_rowmajor(xp[0]), out_f32=out, splits=splits, atomic=splits > 1)
+        return out
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm
+def layernorm_fwd(x, gamma, beta, eps=1e-5, *, save_stats=True):
+    _cuda(x, gamma, beta)
+    rows, d = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    a = capi.LayerNormFwdArgs()
+    a.x, a.gamma, a.beta, a.y, a.mean, a.rstd = _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd)
+    a.rows, a.d, a.seq_len, a.dtype, a.eps = rows, d, 0, _dt(x), eps
+    capi.call("tvt_layernorm_fwd", a, _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dgamma=None, dbeta=None, dbias=None, dropout_p=0.0, seed=0):
+    """Returns (dx, dz): dz is the dropout-masked branch gradient (dz is dx when dropout_p == 0)."""
+    _cuda(dy, x, mean, rstd, gamma, dgamma, dbeta, dbias)
+    rows, d = x.shape
+    dx = torch.empty_like(x)
+    dz = torch.empty_like(x) if dropout_p > 0 else None
+    a = capi.LayerNormBwdArgs()
+    a.dy, a.x, a.mean, a.rstd, a.gamma, a.dx, a.dz = _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dz)
+    a.dgamma, a.dbeta, a.dbias = _p(dgamma), _p(dbeta), _p(dbias)
+    a.rows, a.d, a.seq_len, a.dtype, a.dropout_p, a.dropout_seed = rows, d, 0, _dt(x), dropout_p, seed
+    capi.call("tvt_layernorm_bwd", a, _stream())
+    return dx, (dz if dz is not None else dx)
+
+
+def embed_fwd(feat, cls, pe, gamma, beta, eps=1e-5, dropout_p=0.0, seed=0):
+    """feat [B, T, d], cls [B, d], pe [S, d] fp32 -> tokens [B*S, d], pre-LN rows, mean, rstd."""
+    _cuda(feat, cls, pe, gamma, beta)
+    B, T, d = feat.shape
+    S = T + 1
+    y = torch.empty(B * S, d, dtype=feat.dtype, device=feat.device)
+    pre = torch.empty_like(y)
+    mean = torch.empty(B * S, dtype=torch.float32, device=feat.device)
+    rstd = torch.empty_like(mean)
+    a = capi.LayerNormFwdArgs()
+    a.x, a.cls, a.pe, a.gamma, a.beta, a.y, a.pre, a.mean, a.rstd = (_p(feat), _p(cls), _p(pe), _p(gamma), _p(beta),
+                                                                      _p(y), _p(pre), _p(mean), _p(rstd))
+    a.rows, a.d, a.seq_len, a.dtype, a.eps, a.dropout_p, a.dropout_seed = B * S, d, S, _dt(feat), eps, dropout_p, seed
+    capi.call("tvt_layernorm_fwd", a, _stream())
+    return y, pre, mean, rstd
+
+
+def embed_bwd(dy, pre, mean, rstd, gamma, B, S, *, dgamma, dbeta, dropout_p=0.0, seed=0, need_dfeat=True):
+    d = pre.shape[1]
+    dfeat = torch.empty(B, S - 1, d, dtype=pre.dtype, device=pre.device) if need_dfeat else None
+    dcls = torch.empty(B, d, dtype=pre.dtype, device=pre.device)
+    a = capi.LayerNormBwdArgs()
+    a.dy, a.x, a.mean, a.rstd, a.gamma = _p(dy), _p(pre), _p(mean), _p(rstd), _p(gamma)
+    a.dfeat, a.dcls, a.dgamma, a.dbeta = _p(dfeat), _p(dcls), _p(dgamma), _p(dbeta)
+    a.rows, a.d, a.seq_len, a.dtype, a.dropout_p, a.dropout_seed = B * S, d, S, _dt(pre), dropout_p, seed
+    capi.call("tvt_layernorm_bwd", a, _stream())
+    return dfeat, dcls
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attention_fwd(q, k, v, B, H, Sq, Sk, hd, scale, *, dropout_p=0.0, seed=0, impl=0):
+    """q [B*Sq, >=H*hd] (row pitch q.stride(0)), k/v [B*Sk, ...]; returns o [B*Sq, H*hd], lse [B,H,Sq]."""
+    _cuda(q, k, v)
+    o = torch.empty(B * Sq, H * hd, dtype=q.dtype, device=q.device)
+    lse = torch.empty(B, H, Sq, dtype=torch.float32, device=q.device)
+    a = capi.AttentionFwdArgs()
+    a.q, a.k, a.v, a.o, a.lse = _p(q), _p(k), _p(v), _p(o), _p(lse)
+    a.batch, a.heads, a.sq, a.sk, a.head_dim = B, H, Sq, Sk, hd
+    a.ldq, a.ldk, a.ldv, a.ldo = _rowmajor(q), _rowmajor(k), _rowmajor(v), H * hd
+    a.scale, a.dtype, a.impl, a.dropout_p, a.dropout_seed = scale, _dt(q), impl, dropout_p, seed
+    capi.call("tvt_attention_fwd", a, _stream())
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, Sq, Sk, hd, scale, *, dropout_p=0.0, seed=0, impl=0):
+    _cuda(q, k, v, o, do, lse, dq, dk, dv)
+    a = capi.AttentionBwdArgs()
+    a.q, a.k, a.v, a.o, a.d_o, a.lse, a.dq, a.dk, a.dv = (_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(dq),
+                                                          _p(dk), _p(dv))
+    a.batch, a.heads, a.sq, a.sk, a.head_dim = B, H, Sq, Sk, hd
+    a.ldq, a.ldk, a.ldv, a.ldo, a.lddo = _rowmajor(q), _rowmajor(k), _rowmajor(v), _rowmajor(o), _rowmajor(do)
+    a.lddq, a.lddk, a.lddv = _rowmajor(dq), _rowmajor(dk), _rowmajor(dv)
+    a.scale, a.dtype, a.impl, a.dropout_p, a.dropout_seed = scale, _dt(q), impl, dropout_p, seed
+    capi.call("tvt_attention_bwd", a, _stream())
+
+
+# ------------------------------------------------------------------------------------------ pooling
+def pyramid_pool_fwd(tokens, B, S, d, groups, relu=True, skip_cls=True):
+    """tokens [B*S, d] -> list of out_g [B, floor(T/g)*d] over the frame tokens (CLS row skipped)."""
+    _cuda(tokens)
+    T = S - 1 if skip_cls else S
+    a = capi.PyramidPoolFwdArgs()
+    base = tokens.data_ptr() + (d * tokens.element_size() if skip_cls else 0)
+    a.x, a.batch, a.frames, a.d, a.x_batch_stride, a.x_frame_stride = base, B, T, d, S * d, d
+    a.num_scales, a.dtype, a.relu = len(groups), _dt(tokens), int(relu)
+    outs = []
+    for i, g in enumerate(groups):
+        o = torch.empty(B, (T // g) * d, dtype=tokens.dtype, device=tokens.device)
+        outs.append(o)
+        a.groups[i] = g
+        a.out[i] = o.data_ptr()
+    capi.call("tvt_pyramid_pool_fwd", a, _stream())
+    return outs
+
+
+def pyramid_pool_bwd(douts, outs, dtokens, B, S, d, groups, relu=True, skip_cls=True, accumulate=False):
+    """Writes (or accumulates) the frame-token rows of dtokens [B*S, d]."""
+    _cuda(dtokens, *douts)
+    T = S - 1 if skip_cls else S
+    a = capi.PyramidPoolBwdArgs()
+    base = dtokens.data_ptr() + (d * dtokens.element_size() if skip_cls else 0)
+    a.dx, a.batch, a.frames, a.d, a.dx_batch_stride, a.dx_frame_stride = base, B, T, d, S * d, d
+    a.num_scales, a.dtype, a.relu, a.accumulate = len(groups), _dt(dtokens), int(relu), int(accumulate)
+    for i, g in enumerate(groups):
+        a.groups[i] = g
+        a.dout[i] = douts[i].data_ptr()
+        a.out[i] = outs[i].data_ptr()
+    capi.call("tvt_pyramid_pool_bwd", a, _stream())
+
+
+def spatial_pool(x, out, col_offset):
+    """x [frames, C, H, W] -> out[:, col_offset:col_offset+C] = mean over H*W."""
+    _cuda(x, out)
+    frames, Cc = x.shape[0], x.shape[1]
+    a = capi.SpatialPoolArgs(_p(x), _p(out), frames, Cc, x.shape[2] * x.shape[3], _rowmajor(out), col_offset, _dt(x), _dt(out))
+    capi.call("tvt_spatial_pool_fwd", a, _stream())
+
+
+# ------------------------------------------------------------------------------------------ heads / loss
+def head_linear_fwd(x, w, b):
+    _cuda(x, w, b)
+    M, K = x.shape
+    Cc = w.shape[0]
+    y = torch.empty(M, Cc, dtype=torch.float32, device=x.device)
+    a = capi.HeadLinearFwdArgs(_p(x), _p(w), _p(b), _p(y), M, K, Cc, _dt(x))
+    capi.call("tvt_head_linear_fwd", a, _stream())
+    return y
+
+
+def head_linear_bwd(x, w, dy, need_dx=True):
+    M, K = x.shape
+    Cc = w.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.zeros(Cc, K, dtype=torch.float32, device=x.device)
+    db = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    a = capi.HeadLinearBwdArgs(_p(x), _p(w), _p(dy), _p(dx), _p(dw), _p(db), M, K, Cc, _dt(x))
+    capi.call("tvt_head_linear_bwd", a, _stream())
+    return dx, dw, db
+
+
+def cls_sum(tokens_list, B, S, d):
+    _cuda(*tokens_list)
+    out = torch.empty(B, d, dtype=tokens_list[0].dtype, device=tokens_list[0].device)
+    a = capi.ClsSumArgs()
+    for i, t in enumerate(tokens_list):
+        a.tokens[i] = t.data_ptr()
+    a.out, a.batch, a.seq_len, a.d, a.num_experts, a.dtype = _p(out), B, S, d, len(tokens_list), _dt(out)
+    capi.call("tvt_cls_sum_fwd", a, _stream())
+    return out
+
+
+def distill_loss(student, teacher, target, *, w_bce=1.0, w_ce=0.0, w_kl=0.0, temperature=1.0, grad_scale=1.0,
+                 need_grad=True):
+    """student/teacher/target fp32 [B, C].  Returns (losses[5] = total,bce,ce,kl,cos0 ; dlogits or None)."""
+    _cuda(student, teacher, target)
+    B, Cc = student.shape
+    losses = torch.zeros(5, dtype=torch.float32, device=student.device)
+    dl = torch.empty_like(student) if need_grad else None
+    a = capi.DistillLossArgs(_p(student), _p(teacher), _p(target), _p(losses), _p(dl), B, Cc, w_bce, w_ce, w_kl,
+                             temperature, grad_scale)
+    capi.call("tvt_distill_loss", a, _stream())
+    return losses, dl
+
+
+def pyramid_head(z, target=None, need_grad=False, grad_scale=1.0):
+    """z fp32 [G, B, C] -> prob [B, C] (mean of sigmoids); optional BCE(prob, target) and dz."""
+    _cuda(z, target)
+    G, B, Cc = z.shape
+    prob = torch.empty(B, Cc, dtype=torch.float32, device=z.device)
+    loss = torch.zeros(1, dtype=torch.float32, device=z.device) if target is not None else None
+    dz = torch.empty_like(z) if need_grad else None
+    a = capi.PyramidHeadArgs(_p(z), _p(target), _p(prob), _p(loss), _p(dz), G, B, Cc, grad_scale)
+    capi.call("tvt_pyramid_head", a, _stream())
+    return prob, loss, dz

@@ -23,6 +23,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define TVT_API __attribute__((visibility("default")))
+#else
+#define TVT_API
+#endif
+
 typedef enum {
   TVT_OK = 0,
   TVT_EINVAL = -1,     /* bad shape / alignment / null pointer */
@@ -34,10 +40,10 @@ typedef enum {
 typedef enum { TVT_BF16 = 0, TVT_F32 = 1 } tvt_dtype;
 typedef enum { TVT_ACT_NONE = 0, TVT_ACT_RELU = 1, TVT_ACT_GELU = 2 } tvt_act;
 
-const char* tvt_last_error(void);
-int tvt_version(void);
+TVT_API const char* tvt_last_error(void);
+TVT_API int tvt_version(void);
 /* TVT_OK when the current CUDA device is a B200-class part (compute capability 10.x). */
-int tvt_device_check(void);
+TVT_API int tvt_device_check(void);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators, fused epilogue).
@@ -100,7 +106,276 @@ typedef struct {
   int64_t ld_bf16;
 } tvt_gemm_args;
 
-int tvt_gemm(const tvt_gemm_args* args, void* stream);
+TVT_API int tvt_gemm(const tvt_gemm_args* args, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm forward / backward over the last dimension (eps inside the sqrt, affine), fp32 statistics.
+ * Replaces aten::native_layer_norm(+backward) reached from TransformerEncoderLayer.norm1/norm2
+ * (torch/nn/modules/transformer.py:952-956), SimpleTransformer.norm (src/models/transformer.py:49,80)
+ * and mlp_head[0] (src/models/transformer.py:54).
+ *
+ * Embed mode (seq_len = S > 0) fuses SimpleTransformer.add_pos_cls (src/models/transformer.py:74-82):
+ * output row (b, s) = LN(dropout((s == 0 ? cls[b] : x[b, s-1]) + pe[s])), rows = B * S, tokens laid out
+ * batch-major ([B, S, d]); `pre` optionally receives the pre-LN rows (needed by the backward pass).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;      /* [rows, d]; embed mode: frame features [B, S-1, d] */
+  const void* cls;    /* embed mode: [B, d] */
+  const float* pe;    /* embed mode: [S, d] fp32 */
+  const float* gamma; /* [d] fp32 */
+  const float* beta;  /* [d] fp32 */
+  void* y;            /* [rows, d] */
+  void* pre;          /* embed mode, optional: [rows, d] pre-LN rows */
+  float* mean;        /* optional [rows] */
+  float* rstd;        /* optional [rows] */
+  int64_t rows, d, seq_len;
+  int32_t dtype;      /* tvt_dtype of x / cls / y / pre */
+  float eps;
+  float dropout_p;    /* embed mode only: dropout after the positional encoding */
+  uint64_t dropout_seed;
+} tvt_layernorm_fwd_args;
+TVT_API int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* args, void* stream);
+
+/* dx = LN'(dy); dgamma += sum_rows dy * xhat; dbeta += sum_rows dy (atomics: caller zero-fills).
+ * dz (optional) = dropout-masked dx with the mask of the GEMM epilogue that produced the branch
+ * (element index row * d + col), dbias (optional) += column sums of dz (of dx when dz is NULL).
+ * Embed mode scatters the (dropout-masked) dx rows to dfeat [B, S-1, d] and dcls [B, d]. */
+typedef struct {
+  const void* dy;
+  const void* x;      /* pre-LN input saved by the forward pass */
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  void* dx;
+  void* dz;
+  void* dfeat;
+  void* dcls;
+  float* dgamma;      /* optional */
+  float* dbeta;       /* optional */
+  float* dbias;       /* optional */
+  int64_t rows, d, seq_len;
+  int32_t dtype;
+  float dropout_p;
+  uint64_t dropout_seed;
+} tvt_layernorm_bwd_args;
+TVT_API int tvt_layernorm_bwd(const tvt_layernorm_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scaled-dot-product attention, softmax(Q K^T * scale) V, forward and backward, any Sq / Sk (self- and
+ * cross-modal attention share the kernel).  Replaces aten::scaled_dot_product_attention reached from
+ * F.multi_head_attention_forward (torch/nn/functional.py:6682 via src/models/transformer.py:116) and
+ * the explicit einsum/softmax/einsum of src/models/vit.py:51-55.
+ * Layout: q/k/v/o are 2-D row-major token matrices; token (b, s) is row b * seq + s; head h occupies
+ * columns [h * head_dim, (h+1) * head_dim) starting at the given pointer; ld* are row pitches in
+ * elements (so q/k/v may alias one packed [n, 3d] in-projection output).  lse is [B, H, Sq] fp32.
+ * impl: 0 = auto, 1 = fp32 CUDA-core kernel (any dtype; the fp32 parity mode), 2 = tcgen05 kernel (bf16).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q; const void* k; const void* v;
+  void* o;
+  float* lse;
+  int64_t batch, heads, sq, sk, head_dim;
+  int64_t ldq, ldk, ldv, ldo;
+  float scale;
+  int32_t dtype;
+  int32_t impl;
+  float dropout_p;        /* attention-probability dropout */
+  uint64_t dropout_seed;
+} tvt_attention_fwd_args;
+TVT_API int tvt_attention_fwd(const tvt_attention_fwd_args* args, void* stream);
+
+typedef struct {
+  const void* q; const void* k; const void* v; const void* o; const void* d_o;
+  const float* lse;
+  void* dq; void* dk; void* dv;
+  int64_t batch, heads, sq, sk, head_dim;
+  int64_t ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  float scale;
+  int32_t dtype;
+  int32_t impl;
+  float dropout_p;
+  uint64_t dropout_seed;
+} tvt_attention_bwd_args;
+TVT_API int tvt_attention_bwd(const tvt_attention_bwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Temporal pyramid pooling: all scales of sum_group (src/models/TPN.py:64-72) in one pass, with the
+ * leading nn.ReLU() of Reasoning.relation (src/models/TPN.py:89) fused:
+ *   out_g[b, k*d + j] = relu(sum_{t in [g*k, g*(k+1))} x[b, t, j]),  k < floor(T/g)  (remainder dropped)
+ * x rows are addressed as x + (b * x_batch_stride + t * x_frame_stride) (elements), so the frame
+ * tokens of a [B, S, d] token tensor can be pooled in place (skip the CLS row via the base pointer).
+ * Backward: dx[b,t,:] = sum_g [t < g*floor(T/g)] dout_g[b, t/g, :] * (out_g[b, t/g, :] > 0).
+ * ---------------------------------------------------------------------------------------------- */
+#define TVT_MAX_POOL_SCALES 8
+typedef struct {
+  const void* x;
+  int64_t batch, frames, d;
+  int64_t x_batch_stride, x_frame_stride;
+  int32_t num_scales;
+  int32_t groups[TVT_MAX_POOL_SCALES];
+  void* out[TVT_MAX_POOL_SCALES];  /* out[i]: [B, floor(T/groups[i]) * d] */
+  int32_t dtype;
+  int32_t relu;
+} tvt_pyramid_pool_fwd_args;
+TVT_API int tvt_pyramid_pool_fwd(const tvt_pyramid_pool_fwd_args* args, void* stream);
+
+typedef struct {
+  const void* dout[TVT_MAX_POOL_SCALES];
+  const void* out[TVT_MAX_POOL_SCALES]; /* forward outputs (ReLU mask); ignored when relu = 0 */
+  void* dx;
+  int64_t batch, frames, d;
+  int64_t dx_batch_stride, dx_frame_stride;
+  int32_t num_scales;
+  int32_t groups[TVT_MAX_POOL_SCALES];
+  int32_t dtype;
+  int32_t relu;
+  int32_t accumulate; /* 1: dx += ... (dx already holds another gradient) */
+} tvt_pyramid_pool_bwd_args;
+TVT_API int tvt_pyramid_pool_bwd(const tvt_pyramid_pool_bwd_args* args, void* stream);
+
+/* Spatial pyramid pooling (src/models/TPN.py:2-40): global average of a [frames, C, HW] feature map
+ * over HW -> [frames, C] written at column offset `col_offset` of a [frames, ld_out] matrix, so the
+ * three levels land in the reference's concat order (high, mid, low) (src/models/TPN.py:58). */
+typedef struct {
+  const void* x;
+  void* out;
+  int64_t frames, channels, hw;
+  int64_t ld_out, col_offset;
+  int32_t dtype;     /* of x */
+  int32_t out_dtype;
+} tvt_spatial_pool_args;
+TVT_API int tvt_spatial_pool_fwd(const tvt_spatial_pool_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Classification / distillation loss, forward + gradient in one launch.
+ * Replaces nn.BCEWithLogitsLoss (src/models/transformer.py:35,142; frame_transformer.py:89,251),
+ * nn.CrossEntropyLoss on argmax(teacher) (frame_transformer.py:90,250), nn.CosineSimilarity monitor
+ * (frame_transformer.py:121,257), plus the north-star KL term T^2 * kl_div(log_softmax(s/T),
+ * softmax(t/T), 'batchmean') (torch-pinned extension).
+ *   loss = w_bce * BCE + w_ce * CE + w_kl * KL
+ * losses[0..4] = {total, bce, ce, kl, cos(student, teacher)[0]} (accumulated: caller zero-fills);
+ * dlogits = d total / d student * grad_scale.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* student;  /* [B, C] fp32 logits */
+  const float* teacher;  /* [B, C] or NULL (then w_ce, w_kl must be 0) */
+  const float* target;   /* [B, C] multi-hot */
+  float* losses;         /* [5] */
+  float* dlogits;        /* [B, C] or NULL */
+  int64_t batch, classes;
+  float w_bce, w_ce, w_kl, temperature, grad_scale;
+} tvt_distill_loss_args;
+TVT_API int tvt_distill_loss(const tvt_distill_loss_args* args, void* stream);
+
+/* Reasoning output stage (src/models/TPN.py:98,112): p = mean_g sigmoid(z_g); optional BCE(p, target)
+ * (mean over B*C) accumulated into loss[0], and dz_g = dL/dz_g * grad_scale. z: [G, B, C] fp32. */
+typedef struct {
+  const float* z;
+  const float* target; /* optional */
+  float* prob;         /* [B, C] */
+  float* loss;         /* optional [1], accumulated */
+  float* dz;           /* optional [G, B, C] */
+  int64_t scales, batch, classes;
+  float grad_scale;
+} tvt_pyramid_head_args;
+TVT_API int tvt_pyramid_head(const tvt_pyramid_head_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small helpers on the path.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[c] += sum_rows x[r, c] (fp32 atomics; caller zero-fills). Bias gradients of Linear layers. */
+typedef struct {
+  const void* x;
+  float* out;
+  int64_t rows, cols, ld;
+  int32_t dtype;
+} tvt_colsum_args;
+TVT_API int tvt_colsum(const tvt_colsum_args* args, void* stream);
+
+/* Convert fp32 -> bf16 (hi) and optionally the bf16 residual (lo = bf16(x - hi)); n elements.
+ * Used for weights every step and for activations in the fp32 parity mode. */
+typedef struct {
+  const float* x;
+  void* hi;
+  void* lo; /* optional */
+  int64_t n;
+} tvt_split_args;
+TVT_API int tvt_split_f32(const tvt_split_args* args, void* stream);
+
+/* y = act(x + bias) (+ dropout) elementwise over [rows, cols] fp32 input -> T output (after a split-K
+ * GEMM whose epilogue cannot apply them), and its backward dx = dy * act'(y) (* dropout mask). */
+typedef struct {
+  const float* x;
+  const float* bias; /* [cols] or NULL */
+  void* y;
+  int64_t rows, cols;
+  int32_t out_dtype;
+  int32_t act;
+  float dropout_p;
+  uint64_t dropout_seed;
+} tvt_bias_act_args;
+TVT_API int tvt_bias_act_fwd(const tvt_bias_act_args* args, void* stream);
+
+/* PositionalEncoding.forward (src/models/transformer.py:23-25): y[b, s, :] = dropout(x[b, s, :] + pe[s, :])
+ * on batch-major tokens [B*S, d]; pe fp32 [S, d].  Backward is tvt_act_bwd with act = NONE. */
+typedef struct {
+  const void* x;
+  const float* pe;
+  void* y;
+  int64_t rows, d, seq_len;
+  int32_t dtype;
+  float dropout_p;
+  uint64_t dropout_seed;
+} tvt_posenc_args;
+TVT_API int tvt_posenc_fwd(const tvt_posenc_args* args, void* stream);
+
+/* dx = dy * act'(.) * dropout-mask: backward of y = dropout(act(z)) when no GEMM epilogue can absorb it.
+ * ReLU uses the forward output y (y > 0 covers both the ReLU and the dropped elements); GELU uses the
+ * saved pre-activation z.  Elementwise over [rows, cols], all tensors of dtype `dtype`. */
+typedef struct {
+  const void* dy;
+  const void* y_or_z;
+  void* dx;
+  int64_t rows, cols;
+  int32_t dtype;
+  int32_t act;
+  float dropout_p;
+  uint64_t dropout_seed;
+} tvt_act_bwd_args;
+TVT_API int tvt_act_bwd(const tvt_act_bwd_args* args, void* stream);
+
+/* Skinny linear layer for class heads (N = classes <= 64, not tensor-core shaped):
+ *   y[m, c] = sum_k x[m, k] * w[c, k] + b[c]      (mlp_head[1], src/models/transformer.py:54;
+ *                                                   Reasoning's last Linear, src/models/TPN.py:97)
+ * fwd: x [M, K] (T), w [C, K] fp32, b [C] fp32 -> y [M, C] fp32.
+ * bwd: dy [M, C] fp32 -> dx [M, K] (T), dw [C, K] fp32 (+=), db [C] fp32 (+=) (atomics). */
+typedef struct {
+  const void* x; const float* w; const float* b;
+  float* y;
+  int64_t m, k, classes;
+  int32_t dtype;
+} tvt_head_linear_fwd_args;
+TVT_API int tvt_head_linear_fwd(const tvt_head_linear_fwd_args* args, void* stream);
+typedef struct {
+  const void* x; const float* w; const float* dy;
+  void* dx; float* dw; float* db;
+  int64_t m, k, classes;
+  int32_t dtype;
+} tvt_head_linear_bwd_args;
+TVT_API int tvt_head_linear_bwd(const tvt_head_linear_bwd_args* args, void* stream);
+
+/* CLS gather + expert sum (src/models/transformer.py:123,127-130): out[b, :] = sum_e tok_e[b*S, :];
+ * and the scatter of its gradient back into zero-filled token-gradient tensors. */
+#define TVT_MAX_EXPERTS 8
+typedef struct {
+  const void* tokens[TVT_MAX_EXPERTS]; /* each [B*S, d], CLS = row b*S */
+  void* out;                           /* [B, d] */
+  int64_t batch, seq_len, d;
+  int32_t num_experts;
+  int32_t dtype;
+} tvt_cls_sum_args;
+TVT_API int tvt_cls_sum_fwd(const tvt_cls_sum_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ here; at the reference's own widths ``make_golden.py`` proves the two produce id
 Attribute names match the reference so ``state_dict`` keys are interchangeable.
 """
 import math
+import warnings
 
 import torch
 import torch.nn as nn
@@ -14,13 +15,15 @@ import torch.nn.functional as F
 from torch.nn import TransformerEncoder, TransformerEncoderLayer
 
 
+def _stack(layer, nlayers):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # "enable_nested_tensor is True, but ..." (seq-first layers)
+        return TransformerEncoder(layer, nlayers)
+
+
 def _encoder(d, nhead, nhid, dropout, nlayers):
     # src/models/transformer.py:39-47 — default TransformerEncoderLayer: ReLU, post-norm, seq-first, eps 1e-5.
-    import warnings
-
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        return TransformerEncoder(TransformerEncoderLayer(d, nhead, nhid, dropout), nlayers)
+    return _stack(TransformerEncoderLayer(d, nhead, nhid, dropout), nlayers)
 
 
 class PositionalEncoding(nn.Module):
@@ -57,8 +60,11 @@ class SimpleTransformer(nn.Module):
         self.seq_len = seq_len + (1 if cls else 0)                      # transformer.py:33-34
         self.criterion = nn.BCEWithLogitsLoss()                         # :35
         self.position_encoder = PositionalEncoding(d, dropout, max_len=self.seq_len)  # :36-37
-        self.transformer_encoder0 = _encoder(d, nhead, nhid, dropout, nlayers)       # :39-42
-        self.transformer_encoder1 = _encoder(d, nhead, nhid, dropout, nlayers)       # :44-47
+        # :39-47 — the template layers stay registered (extra state_dict keys encoder_layers{0,1}.*)
+        self.encoder_layers0 = TransformerEncoderLayer(d, nhead, nhid, dropout)
+        self.transformer_encoder0 = _stack(self.encoder_layers0, nlayers)
+        self.encoder_layers1 = TransformerEncoderLayer(d, nhead, nhid, dropout)
+        self.transformer_encoder1 = _stack(self.encoder_layers1, nlayers)
         self.norm = nn.LayerNorm(d)                                     # :49
         self.cls = nn.Parameter(torch.rand(1, batch_size, d))           # :52-53 one CLS per batch slot
         self.mlp_head = nn.Sequential(nn.LayerNorm(d), nn.Linear(d, n_classes))      # :54

@@ -1,0 +1,227 @@
+"""GPU: the reference-facing modules (tvt_b200.hostapi) against the CPU-restated oracle (oracle/param.py)
+run in fp32 on the same device, weights copied through state_dict, identical seeded inputs, dropout 0.
+Bars (BASELINE.json north_star): fp32-accumulate mode 1e-3, bf16 mode 2e-2 (normwise relative) on logits
+and on every parameter gradient; top-1 agreement >= 99.9 % on a fixed synthetic clip set."""
+import os
+
+import pytest
+import torch
+
+from util import assert_close, copy_state, grads_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = {"fp32": 1e-3, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def api():
+    import tvt_b200
+    from tvt_b200 import hostapi
+    assert tvt_b200.capi.load().tvt_device_check() == 0
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return hostapi
+
+
+def _targets(B, C, gen):
+    y = (torch.rand(B, C, generator=gen) < 0.15).float()
+    y[torch.arange(B), torch.randint(0, C, (B,), generator=gen)] = 1.0       # loader forces one positive
+    return y
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_simple_transformer_ptn_parity(api, precision):
+    from oracle import param
+    cfg = dict(batch_size=4, seq_len=16, cls=1, dropout=0.0, input_dimension=256, nhead=4, nhid=512, nlayers=2,
+               model="ptn", learning_rate=1e-3, momentum=0.0, weight_decay=0.0, n_classes=15)
+    torch.manual_seed(1130)
+    ref = param.SimpleTransformer(**cfg).to(DEV)
+    mod = copy_state(api.SimpleTransformer(precision=precision, **cfg), ref).to(DEV)
+    gen = torch.Generator().manual_seed(1130)
+    x = torch.randn(4, 16, 3, 256, generator=gen).to(DEV)                   # third expert bypasses the encoders
+    y = _targets(4, 15, gen).to(DEV)
+    lr = ref.criterion(ref.ptn(x), y)
+    lr.backward()
+    loss = mod.training_step({"experts": x, "label": y}, 0)
+    loss.backward()
+    assert_close(mod.ptn(x), ref.ptn(x), TOL[precision], "logits")
+    assert_close(loss, lr, TOL[precision], "loss")
+    worst = grads_close(mod, ref, TOL[precision], "ptn ", skip=("mlp_encoder", "encoder_layers"))
+    print("worst grad", precision, worst)
+
+
+def test_drop_in_at_reference_width_matches_golden(api):
+    """Same constructor call as the reference (d = 2048 hard-coded there) reproduces the frozen reference logits."""
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.pt"), weights_only=False)
+    g = gold["ptn"]
+    torch.manual_seed(gold["seed"])
+    mod = api.SimpleTransformer(precision="fp32", **g["cfg"]).to(DEV)        # same RNG stream as the reference
+    assert sorted(mod.state_dict().keys()) == g["state_dict_keys"]
+    gen = torch.Generator().manual_seed(gold["seed"])
+    x = torch.randn(2, 4, 3, 2048, generator=gen).to(DEV)
+    y = (torch.rand(2, 15, generator=gen) < 0.15).float().to(DEV)
+    logits = mod.ptn(x)
+    assert_close(logits, g["logits"], 1e-3, "golden logits")
+    loss = mod.training_step({"experts": x, "label": y}, 0)
+    assert_close(loss, g["loss"], 1e-3, "golden loss")
+    loss.backward()
+    for name, p in mod.named_parameters():
+        if name in g["grad_norms"] and float(g["grad_norms"][name]) > 0:
+            got = p.grad.double().norm().item()
+            want = float(g["grad_norms"][name])
+            assert abs(got - want) <= 2e-3 * want, (name, got, want)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("fusion,pyramid", [("sum", False), ("cross", False), ("cross", True)])
+def test_fusion_transformer_parity(api, precision, fusion, pyramid):
+    from oracle import param
+    kw = dict(in_dims=(2048, 1024, 128), d=256, nhead=4, nhid=512, nlayers=2, dropout=0.0, batch_size=6, frames=20,
+              n_classes=15, fusion=fusion, pyramid=pyramid)
+    torch.manual_seed(1130)
+    ref = param.FusionTransformer(**kw).to(DEV)
+    mod = copy_state(api.FusionTransformer(precision=precision, **kw), ref).to(DEV)
+    gen = torch.Generator().manual_seed(1130)
+    xs = [torch.relu(torch.randn(6, 20, D, generator=gen) * 0.5).to(DEV) if D > 128 else torch.randn(6, 20, D, generator=gen).to(DEV)
+          for D in kw["in_dims"]]
+    y = _targets(6, 15, gen).to(DEV)
+    logits_r, pyr_r = ref(xs)
+    loss_r = torch.nn.functional.binary_cross_entropy_with_logits(logits_r, y)
+    if pyramid:
+        loss_r = loss_r + torch.nn.functional.binary_cross_entropy(pyr_r, y)
+    loss_r.backward()
+    logits, prob, ploss = mod(xs, y)
+    from tvt_b200.functions import DistillLossFn
+    loss = DistillLossFn.apply(logits, None, y, 1.0, 0.0, 0.0, 1.0)[0]
+    if pyramid:
+        loss = loss + ploss[0]
+        assert_close(prob, pyr_r, TOL[precision], "pyramid probs")
+    loss.backward()
+    assert_close(logits, logits_r, TOL[precision], "logits")
+    assert_close(loss, loss_r, TOL[precision], "loss")
+    worst = grads_close(mod, ref, TOL[precision], f"{fusion} ")
+    print("worst grad", precision, fusion, pyramid, worst)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_distillation_step_parity(api, precision):
+    """Frozen 3-expert cross-attention teacher -> RGB-only pyramid student, BCE + CE + KL + pyramid BCE."""
+    from oracle import param
+    common = dict(d=256, nhead=4, nhid=512, nlayers=2, dropout=0.0, batch_size=8, frames=16, n_classes=15)
+    torch.manual_seed(1130)
+    t_ref = param.FusionTransformer(in_dims=(2048, 1024, 128), fusion="cross", **common).to(DEV).eval()
+    s_ref = param.FusionTransformer(in_dims=(2048,), fusion="sum", pyramid=True, **common).to(DEV)
+    teacher = copy_state(api.FusionTransformer(in_dims=(2048, 1024, 128), fusion="cross", precision=precision, **common), t_ref).to(DEV)
+    student = copy_state(api.FusionTransformer(in_dims=(2048,), fusion="sum", pyramid=True, precision=precision, **common), s_ref).to(DEV)
+    trainer = api.DistillationTrainer(teacher, student, temperature=2.0, alpha=0.5).train()
+    gen = torch.Generator().manual_seed(1130)
+    xs = [torch.randn(8, 16, D, generator=gen).to(DEV) for D in (2048, 1024, 128)]
+    y = _targets(8, 15, gen).to(DEV)
+    with torch.no_grad():
+        t_logits, _ = t_ref(xs)
+    s_logits, s_pyr = s_ref(xs[:1])
+    loss_r, _ = param.distill_loss(s_logits, t_logits, y, temperature=2.0, alpha=0.5, pyramid=s_pyr)
+    loss_r.backward()
+    loss = trainer.training_step({"experts": xs, "label": y})
+    loss.backward()
+    assert_close(loss, loss_r, TOL[precision], "distillation loss")
+    grads_close(student, s_ref, TOL[precision], "student ")
+    assert all(p.grad is None for p in teacher.parameters())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_frame_stream_parity(api, precision):
+    """FrameTransformer's real widths: d = 896, 2 heads (head_dim 448), ff = 512, 14 scene tokens, GELU head."""
+    from oracle import param
+    kw = dict(d=896, nhead=2, nhid=512, nlayers=2, dropout=0.0, seq_len=14, n_classes=19)
+    torch.manual_seed(1130)
+    ref = param.FrameStream(**kw).to(DEV)
+    mod = copy_state(api.FrameStream(precision=precision, **kw), ref).to(DEV)
+    gen = torch.Generator().manual_seed(1130)
+    feats = torch.randn(4, 14, 896, generator=gen).to(DEV)
+    y = _targets(4, 19, gen).to(DEV)
+    teacher = torch.randn(4, 19, generator=gen).to(DEV)
+    loss_r, _ = param.distill_loss(ref(feats), teacher, y)
+    loss_r.backward()
+    loss = mod.training_step((y, feats), 0, teacher_logits=teacher)
+    loss.backward()
+    assert_close(mod(feats), ref(feats), TOL[precision], "logits")
+    assert_close(loss, loss_r, TOL[precision], "loss")
+    grads_close(mod, ref, TOL[precision], "frame ")
+    # seq-first reference signature of TransformerBase
+    x = torch.randn(14, 4, 896, generator=gen).to(DEV)
+    assert_close(mod.distil_transformer(x), ref.distil_transformer(x), TOL[precision], "TransformerBase.forward")
+
+
+def test_reasoning_and_spatial_pyramid_modules(api):
+    from oracle import param
+    torch.manual_seed(1130)
+    ref = param.Reasoning(num_segments=4, num_frames=5, num_class=15, img_dim=896).to(DEV).eval()
+    mod = copy_state(api.Reasoning(num_segments=4, num_frames=5, num_class=15, img_dim=896, precision="fp32"), ref).to(DEV).eval()
+    gen = torch.Generator().manual_seed(1130)
+    x = torch.randn(3, 20, 896, generator=gen).to(DEV)
+    assert_close(mod(x), ref(x), 1e-3, "Reasoning")
+    assert_close(api.sum_group(x, 3), param.sum_group(x, 3), 1e-6, "sum_group")
+    sp_ref = param.SpatialPyramid().to(DEV)
+    sp = copy_state(api.SpatialPyramid(), sp_ref).to(DEV)
+    maps = [torch.randn(4, c, s, s, generator=gen).to(DEV) for c, s in ((128, 28), (256, 14), (512, 7))]
+    assert_close(sp(*maps), sp_ref(*maps), 1e-3, "SpatialPyramid")
+
+
+def test_top1_agreement_on_fixed_clip_set(api):
+    """>= 99.9 % of argmax predictions agree between the bf16 kernels and the fp32 oracle."""
+    from oracle import param
+    kw = dict(in_dims=(512,), d=256, nhead=4, nhid=512, nlayers=2, dropout=0.0, batch_size=256, frames=16, n_classes=15, fusion="sum")
+    torch.manual_seed(1130)
+    ref = param.FusionTransformer(**kw).to(DEV).eval()
+    with torch.no_grad():
+        ref.mlp_head[1].weight.mul_(8.0)            # trained-model-like logit spread (random init is near-tied)
+    mod = copy_state(api.FusionTransformer(precision="bf16", **kw), ref).to(DEV).eval()
+    gen = torch.Generator().manual_seed(1130)
+    agree = total = 0
+    with torch.no_grad():
+        for _ in range(16):                         # 4096 clips
+            x = torch.relu(torch.randn(256, 16, 512, generator=gen) * 0.5).to(DEV)
+            a = mod([x])[0].argmax(-1)
+            lr = ref([x])[0]
+            b = lr.argmax(-1)
+            top2 = lr.topk(2, dim=-1).values
+            decided = (top2[:, 0] - top2[:, 1]) > 1e-3 * top2[:, 0].abs().clamp_min(1.0)   # ignore numerical ties
+            agree += int(((a == b) | ~decided).sum())
+            total += 256
+    assert agree / total >= 0.999, f"top-1 agreement {agree}/{total}"
+
+
+def test_training_mode_dropout_runs_and_is_consistent(api):
+    """dropout > 0: forward/backward run, are finite, and the recomputed masks make the step self-consistent:
+    a directional finite difference of the loss (same seeds) matches the analytic gradient."""
+    from tvt_b200 import functions
+    kw = dict(in_dims=(256,), d=256, nhead=4, nhid=512, nlayers=1, dropout=0.5, batch_size=8, frames=16, n_classes=15, fusion="sum")
+    torch.manual_seed(3)
+    mod = api.FusionTransformer(precision="fp32", **kw).to(DEV).train()
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 16, 256, generator=gen).to(DEV)
+    y = _targets(8, 15, gen).to(DEV)
+
+    def loss_at():
+        functions._seed_counter[0] = 1000          # replay the same dropout masks
+        logits, _, _ = mod([x], None)
+        return functions.DistillLossFn.apply(logits, None, y, 1.0, 0.0, 0.0, 1.0)[0]
+
+    l0 = loss_at()
+    l0.backward()
+    assert torch.isfinite(l0)
+    w = mod.streams[0].transformer_encoder.layers[0].linear2.weight
+    gdir = torch.randn(w.shape, generator=gen).to(DEV)
+    gdir /= gdir.norm()
+    analytic = float((w.grad * gdir).sum())
+    eps = 1e-2
+    with torch.no_grad():
+        w.add_(eps * gdir); lp = float(loss_at()); w.sub_(2 * eps * gdir); lm = float(loss_at()); w.add_(eps * gdir)
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - analytic) <= 0.05 * max(abs(analytic), 1e-4) + 1e-5, (fd, analytic)
+    # eval mode is deterministic and differs from train mode
+    mod.eval()
+    a, b = mod([x])[0], mod([x])[0]
+    assert torch.equal(a, b)
