@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Headline benchmark: train clips/sec (forward + backward + optimizer step) of the temporal video
+transformer hot path on N B200s, clip-batch data parallel (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c3|c2|c1] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job clips/s with the step's inputs already resident in
+HBM; `e2e` = the same step driven from pinned HOST batches (host->device copy of every step's inputs and
+a device->host read of the loss inside the timed region, copies prefetched on a side stream).
+`roofline` describes the dominant kernel (the tcgen05 GEMM) from a CUDA-event-instrumented step run after
+the timed region; `cpu_baseline` times the CPU oracle (oracle/param.py, the reference's torch.nn
+composition) on a bounded sample of the same workload on this box's host cores.
+`--impl reference` times that CPU oracle alone and prints the same line shape with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# BASELINE.json configs: per-GPU clips, frames, width, layers, heads, ff
+WORKLOADS = {
+    "c1": dict(desc="C1 single-modality 4-layer d=512 encoder, 16 frames x 2048-d RGB, batch 8", batch=8, frames=16, d=512,
+               layers=4, heads=8, ff=2048, teacher=None, student_dims=(2048,), pyramid=False, distill=False),
+    "c2": dict(desc="C2 cross-attention fusion of 3 expert streams (2048/1024/128-d), 32 frames, batch 64", batch=64, frames=32,
+               d=512, layers=4, heads=8, ff=2048, teacher=None, student_dims=(2048, 1024, 128), pyramid=False, distill=False,
+               fusion="cross"),
+    "c3": dict(desc="C3 pyramid network (groups 2,3,4) over 64 frames, batch 128", batch=128, frames=64, d=512, layers=4,
+               heads=8, ff=2048, teacher=None, student_dims=(512,), pyramid=True, distill=False),
+    "c4": dict(desc="C4 frozen 3-expert teacher -> RGB student distillation (KL+CE), 32 frames, 256 clips/GPU", batch=256,
+               frames=32, d=512, layers=4, heads=8, ff=2048, teacher=(2048, 1024, 128), student_dims=(2048,), pyramid=False,
+               distill=True),
+    "c5": dict(desc="C5 pyramid + cross-attention teacher + distillation, 128 frames, d=768, 12 layers, 256 clips/GPU "
+                    "(global batch 2048 on 8 GPUs)", batch=256, frames=128, d=768, layers=12, heads=12, ff=3072,
+               teacher=(2048, 1024, 128), student_dims=(2048,), pyramid=True, distill=True),
+}
+N_CLASSES = 15
+
+
+def flops_per_clip(w):
+    """Algorithmic FLOPs per clip per training step: 3x forward for trained nets,
+    1x for the frozen teacher; attention counted un-padded."""
+    T, d, L, ff = w["frames"], w["d"], w["layers"], w["ff"]
+    S = T + 1
+
+    def net(dims, fusion, pyramid):
+        f = 0.0
+        for D in dims:
+            f += 2 * T * D * d                                           # input projection
+            f += L * (2 * S * d * 3 * d + 2 * S * d * d + 4 * S * d * ff)  # encoder GEMMs
+            f += L * 4 * S * S * d                                       # attention
+        if fusion == "cross" and len(dims) > 1:
+            E = len(dims)
+            f += 4 * S * d * d + 4 * (E - 1) * S * d * d + 4 * S * (E - 1) * S * d + 4 * S * d * ff
+        if pyramid:
+            for g in (2, 3, 4):
+                f += 2 * d * (T // g) * 512 + 2 * 512 * 512 + 2 * 512 * N_CLASSES
+        return f + 2 * d * N_CLASSES
+
+    student = net(w["student_dims"], w.get("fusion", "sum"), w["pyramid"])
+    teacher = net(w["teacher"], "cross", False) if w["teacher"] else 0.0
+    return 3 * student + teacher
+
+
+def synth_batch(w, batch, seed, device="cpu", pin=False):
+    """Synthetic expert features: post-ReLU-like non-negative RGB / motion features,
+    raw Gaussian audio, 30 % of (clip, frame, expert) vectors zeroed like the loader's augmentation;
+    multi-hot labels with at least one positive."""
+    g = torch.Generator().manual_seed(seed)
+    dims = w["teacher"] if w["teacher"] else w["student_dims"]
+    xs = []
+    for D in dims:
+        x = torch.randn(batch, w["frames"], D, generator=g)
+        if D > 128:
+            x = torch.relu(x * 0.5)
+        keep = (torch.rand(batch, w["frames"], 1, generator=g) >= 0.3).float()
+        xs.append(x * keep)
+    y = (torch.rand(batch, N_CLASSES, generator=g) < 0.15).float()
+    y[torch.arange(batch), torch.randint(0, N_CLASSES, (batch,), generator=g)] = 1.0
+    if pin:
+        xs = [x.pin_memory() for x in xs]
+        y = y.pin_memory()
+    if device != "cpu":
+        xs = [x.to(device) for x in xs]
+        y = y.to(device)
+    return xs, y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU oracle arm
+def build_oracle(w, batch):
+    from oracle import param
+    common = dict(d=w["d"], nhead=w["heads"], nhid=w["ff"], nlayers=w["layers"], dropout=0.5, batch_size=batch, frames=w["frames"],
+                  n_classes=N_CLASSES)
+    torch.manual_seed(1130)
+    teacher = param.FusionTransformer(in_dims=w["teacher"], fusion="cross", **common).eval() if w["teacher"] else None
+    student = param.FusionTransformer(in_dims=w["student_dims"], fusion=w.get("fusion", "sum"), pyramid=w["pyramid"], **common).train()
+    return teacher, student
+
+
+def oracle_step(w, teacher, student, opt, xs, y):
+    from oracle import param
+    opt.zero_grad(set_to_none=False)
+    if teacher is not None:
+        with torch.no_grad():
+            t_logits, _ = teacher(xs)
+        s_logits, pyr = student(xs[:len(w["student_dims"])])
+        loss, _ = param.distill_loss(s_logits, t_logits, y, temperature=2.0, alpha=1.0, pyramid=pyr)
+    else:
+        s_logits, pyr = student(xs)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(s_logits, y)
+        if pyr is not None:
+            loss = loss + torch.nn.functional.binary_cross_entropy(pyr, y)
+    loss.backward()
+    opt.step()
+    return float(loss.detach())
+
+
+def time_oracle(w, sample_clips, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    teacher, student = build_oracle(w, sample_clips)
+    opt = torch.optim.AdamW(student.parameters(), lr=1e-4, weight_decay=0.01)
+    xs, y = synth_batch(w, sample_clips, 1130)
+    for _ in range(warmup):
+        oracle_step(w, teacher, student, opt, xs, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(w, teacher, student, opt, xs, y)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_clips / dt, dt, cores
+
+
+def run_reference(args, w, rank):
+    if rank != 0:
+        return
+    sample = args.cpu_clips or max(1, min(w["batch"], int(2.5e11 / flops_per_clip(w)) or 1))
+    cps, dt, cores = time_oracle(w, sample, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "train clips/sec fwd+bwd", "value": round(cps, 3), "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": w["desc"], "sample_clips_per_step": sample, "optimizer": "AdamW", "device": "host CPU"},
+            "cpu_baseline": {"value": round(cps, 3), "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} clips/step of the same workload (oracle/param.py, torch {torch.__version__} CPU, fp32)"},
+            "e2e": {"value": round(cps, 3), "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def build_model(w, batch, precision, dropout, device):
+    from tvt_b200 import hostapi
+    common = dict(d=w["d"], nhead=w["heads"], nhid=w["ff"], nlayers=w["layers"], dropout=dropout, batch_size=batch,
+                  frames=w["frames"], n_classes=N_CLASSES, precision=precision)
+    torch.manual_seed(1130)
+    student = hostapi.FusionTransformer(in_dims=w["student_dims"], fusion=w.get("fusion", "sum"), pyramid=w["pyramid"], **common).to(device)
+    if w["teacher"]:
+        teacher = hostapi.FusionTransformer(in_dims=w["teacher"], fusion="cross", **common).to(device)
+        return hostapi.DistillationTrainer(teacher, student, temperature=2.0, alpha=1.0).train()
+    return student.train()
+
+
+def gpu_step(w, model, reducer, opt, xs, y):
+    from tvt_b200.functions import DistillLossFn
+    reducer.zero_grad()
+    if w["teacher"]:
+        loss = model.training_step({"experts": xs, "label": y})
+    else:
+        logits, _, ploss = model(xs, y if w["pyramid"] else None)
+        loss = DistillLossFn.apply(logits, None, y, 1.0, 0.0, 0.0, 1.0)[0]
+        if ploss is not None:
+            loss = loss + ploss[0]
+    loss.backward()
+    reducer.finish()
+    opt.step()
+    return loss
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="tvt", choices=["tvt", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dropout", type=float, default=0.5, help="config.yaml dropout (0.5 in the reference)")
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's)")
+    ap.add_argument("--cpu-clips", type=int, default=0, help="clips per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default="", help="write the per-kernel CUDA-event breakdown to this file")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["batch"] = args.batch
+    args.warmup = max(args.warmup, 3) if args.impl == "tvt" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    import torch.distributed as dist
+    import tvt_b200
+    from tvt_b200 import capi, ddp
+    rank, local, world = ddp.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the tvt arm has no CPU path (use --impl reference for the CPU oracle)")
+    dev = torch.device("cuda", local)
+    capi.load()
+    if capi.load().tvt_device_check() != 0:
+        raise SystemExit("bench.py: " + capi.last_error())
+    B = w["batch"]
+    model = build_model(w, B, args.precision, args.dropout, dev)
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    reducer = ddp.GradBucketReducer(trainable, bucket_bytes=32 << 20)
+    opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=0.01, fused=True)
+
+    # two resident batches (alternated) + the same two as pinned host batches for the e2e leg
+    host = [synth_batch(w, B, 1130 + rank + 1000 * i, pin=True) for i in range(2)]
+    resident = [([x.to(dev) for x in xs], y.to(dev)) for xs, y in host]
+    h2d_bytes = sum(x.numel() * 4 for x in host[0][0]) + host[0][1].numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_one, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            run_one(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps
+
+    # ---- leg 1: inputs resident in HBM
+    for i in range(args.warmup):
+        gpu_step(w, model, reducer, opt, *resident[i % 2])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = capi.launches
+    ms = timed(lambda i: gpu_step(w, model, reducer, opt, *resident[i % 2]), args.steps)
+    launches = (capi.launches - l0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- leg 2: end to end from pinned host batches, copies prefetched on a side stream
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [None, None]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            xs, y = host[i % 2]
+            slots[i % 2] = ([x.to(dev, non_blocking=True) for x in xs], y.to(dev, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    losses = []
+    state = {"ev": None}
+
+    def e2e_one(i):
+        if state["ev"] is None:
+            state["ev"] = prefetch(i)
+        torch.cuda.current_stream().wait_event(state["ev"])
+        xs, y = slots[i % 2]
+        state["ev"] = prefetch(i + 1)                       # next step's inputs copy while this step computes
+        loss = gpu_step(w, model, reducer, opt, xs, y)
+        for t in xs:
+            t.record_stream(torch.cuda.current_stream())
+        losses.append(loss.item())                          # device -> host read of the step's result
+
+    e2e_one(0)
+    state["ev"] = None
+    ms_e2e = timed(e2e_one, args.steps)
+
+    # ---- instrumented step: CUDA events around every kernel-launching C-ABI call (not part of the timings)
+    breakdown = capi.profile_step(lambda: gpu_step(w, model, reducer, opt, *resident[0]))
+    gemm = breakdown.get("tvt_gemm", {"ms": 0.0, "flops": 0.0, "calls": 0})
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    total_ms = sum(v["ms"] for v in breakdown.values()) or 1.0
+    fl = flops_per_clip(w)
+    value = world * B / (ms * 1e-3)
+    line = {
+        "metric": "train clips/sec fwd+bwd", "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": w["desc"], "clips_per_gpu": B, "global_batch": world * B, "frames": w["frames"], "d_model": w["d"],
+                   "layers": w["layers"], "heads": w["heads"], "ff": w["ff"], "dropout": args.dropout, "optimizer": "AdamW (fused)",
+                   "parallelism": f"dp{world}", "l2": "inputs larger than L2 (%.0f MB per step, two alternating batches)" % (h2d_bytes / 1e6),
+                   "gflop_per_clip_step": round(fl / 1e9, 2)},
+        "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e, 3)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "model_tflops": round(value / world * fl / 1e12, 1),
+        "model_frac_of_peak": round(value / world * fl / 1e12 / peak_tf, 4),
+        "roofline": {"kernel": "tvt::gemm::gemm_kernel (tcgen05)", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                     "launches_per_step": gemm["calls"], "share_of_kernel_time": round(gemm["ms"] / total_ms, 4)},
+    }
+    if not args.no_cpu_baseline:
+        sample = args.cpu_clips or max(1, min(B, int(2.5e11 / fl) or 1))
+        cps, dt, cores = time_oracle(w, sample, 2, 1)
+        line["cpu_baseline"] = {"value": round(cps, 3), "unit": "clips/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} clips/step x 2 steps of the same workload (oracle/param.py on torch CPU, fp32)"}
+    if args.breakdown:
+        with open(args.breakdown, "w") as f:
+            f.write(f"# per-kernel CUDA-event breakdown of one instrumented step ({w['desc']}); ms_per_step timed = {ms:.3f}\n")
+            for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"]):
+                tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] else 0.0
+                f.write(f"{k:28s} calls={v['calls']:5d}  ms={v['ms']:9.3f}  share={v['ms'] / total_ms:6.3f}  TFLOP/s={tf:8.1f}\n")
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -173,10 +173,52 @@ def last_error():
     return load().tvt_last_error().decode(errors="replace")
 
 
+_profile = None  # list of (name, start event, end event, flops) while profile_step() is active
+
+
+def _flops(name, a):
+    if name == "tvt_gemm":
+        return 2.0 * a.m * a.n * a.k * (3 if a.a_lo else 1)
+    if name == "tvt_attention_fwd":
+        return 4.0 * a.batch * a.heads * a.sq * a.sk * a.head_dim
+    if name == "tvt_attention_bwd":
+        return 10.0 * a.batch * a.heads * a.sq * a.sk * a.head_dim
+    return 0.0
+
+
 def call(name, args, stream):
     """Invoke entry point ``name`` with a filled args Structure on cudaStream_t ``stream`` (int)."""
     global launches
-    rc = getattr(load(), name)(C.byref(args), vp(stream))
+    fn = getattr(load(), name)
+    if _profile is None:
+        rc = fn(C.byref(args), vp(stream))
+    else:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(C.byref(args), vp(stream))
+        e1.record()
+        _profile.append((name, e0, e1, _flops(name, args)))
     if rc != 0:
         raise TvtError(f"{name} failed with status {rc}: {last_error()}")
     launches += 1
+
+
+def profile_step(fn):
+    """Run ``fn`` once with CUDA events around every kernel-launching entry point (on torch's current
+    stream, where the kernels are launched) and return {entry point: {ms, flops, calls}}."""
+    global _profile
+    import torch
+    _profile = []
+    try:
+        fn()
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, fl in _profile:
+            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "calls": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["calls"] += 1
+        return out
+    finally:
+        _profile = None

@@ -1,0 +1,92 @@
+"""Clip-batch data parallelism: one process per GPU, replicated parameters, gradients all-reduced over
+NCCL (NVLink 5 / NVSwitch) in flat fp32 buckets that are launched from autograd hooks while the rest of
+the backward pass is still running (the reference has no multi-GPU path at all: pl.Trainer(gpus=1),
+src/main.py:87-88; the oracle for this module is "single process on the concatenated batch").
+
+Parameters' ``.grad`` tensors are views into the flat buckets, so there is no gather/scatter copy: the
+wgrad kernels' outputs are accumulated by autograd straight into the communication buffer.  Buckets are
+filled in reverse registration order (the order backward produces gradients).  Works with any
+torch.distributed backend (NCCL on GPUs; gloo in the CPU tests of the bucketing logic).
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradBucketReducer:
+    def __init__(self, params, bucket_bytes=32 << 20, process_group=None, average=True):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.average = average
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.buckets = []          # list of dict(flat, params, pending, handle)
+        self._index = {}
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):                      # backward order
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self._make_bucket(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self._make_bucket(cur)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    def _make_bucket(self, ps):
+        n = sum(p.numel() for p in ps)
+        flat = torch.zeros(n, dtype=torch.float32, device=ps[0].device)
+        off = 0
+        b = {"flat": flat, "params": list(ps), "pending": len(ps), "handle": None}
+        for p in ps:
+            if p.dtype != torch.float32:
+                raise TypeError("GradBucketReducer expects fp32 master parameters")
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            self._index[id(p)] = b
+        self.buckets.append(b)
+
+    def zero_grad(self):
+        """Zero every bucket (one memset per bucket) and re-arm the hooks; call before each backward."""
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"] = len(b["params"])
+            b["handle"] = None
+
+    def _on_grad(self, p):
+        b = self._index[id(p)]
+        b["pending"] -= 1
+        if b["pending"] == 0 and self.world > 1:
+            # async: NCCL's stream waits on the producer stream, backward keeps going on the compute stream
+            b["handle"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        """Wait for every bucket, reduce the ones whose hooks never fired (unused params), average."""
+        for b in self.buckets:
+            if self.world > 1:
+                if b["handle"] is None:
+                    b["handle"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                b["handle"].wait()
+                if self.average:
+                    b["flat"].mul_(1.0 / self.world)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+
+
+def init_from_env(backend=None):
+    """torchrun-style initialisation (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*); returns (rank, local, world)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, local, world

@@ -33,14 +33,15 @@ def _targets(B, C, gen):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_simple_transformer_ptn_parity(api, precision):
     from oracle import param
-    cfg = dict(batch_size=4, seq_len=16, cls=1, dropout=0.0, input_dimension=256, nhead=4, nhid=512, nlayers=2,
+    B = 4 if precision == "fp32" else 48        # bf16: enough tokens that ReLU-gate flips average out (tools/diag_bf16.py)
+    cfg = dict(batch_size=B, seq_len=16, cls=1, dropout=0.0, input_dimension=256, nhead=4, nhid=512, nlayers=2,
                model="ptn", learning_rate=1e-3, momentum=0.0, weight_decay=0.0, n_classes=15)
     torch.manual_seed(1130)
     ref = param.SimpleTransformer(**cfg).to(DEV)
     mod = copy_state(api.SimpleTransformer(precision=precision, **cfg), ref).to(DEV)
     gen = torch.Generator().manual_seed(1130)
-    x = torch.randn(4, 16, 3, 256, generator=gen).to(DEV)                   # third expert bypasses the encoders
-    y = _targets(4, 15, gen).to(DEV)
+    x = torch.randn(B, 16, 3, 256, generator=gen).to(DEV)                   # third expert bypasses the encoders
+    y = _targets(B, 15, gen).to(DEV)
     lr = ref.criterion(ref.ptn(x), y)
     lr.backward()
     loss = mod.training_step({"experts": x, "label": y}, 0)
@@ -77,15 +78,16 @@ def test_drop_in_at_reference_width_matches_golden(api):
 @pytest.mark.parametrize("fusion,pyramid", [("sum", False), ("cross", False), ("cross", True)])
 def test_fusion_transformer_parity(api, precision, fusion, pyramid):
     from oracle import param
-    kw = dict(in_dims=(2048, 1024, 128), d=256, nhead=4, nhid=512, nlayers=2, dropout=0.0, batch_size=6, frames=20,
+    B = 6 if precision == "fp32" else 48
+    kw = dict(in_dims=(2048, 1024, 128), d=256, nhead=4, nhid=512, nlayers=2, dropout=0.0, batch_size=B, frames=20,
               n_classes=15, fusion=fusion, pyramid=pyramid)
     torch.manual_seed(1130)
     ref = param.FusionTransformer(**kw).to(DEV)
     mod = copy_state(api.FusionTransformer(precision=precision, **kw), ref).to(DEV)
     gen = torch.Generator().manual_seed(1130)
-    xs = [torch.relu(torch.randn(6, 20, D, generator=gen) * 0.5).to(DEV) if D > 128 else torch.randn(6, 20, D, generator=gen).to(DEV)
+    xs = [torch.relu(torch.randn(B, 20, D, generator=gen) * 0.5).to(DEV) if D > 128 else torch.randn(B, 20, D, generator=gen).to(DEV)
           for D in kw["in_dims"]]
-    y = _targets(6, 15, gen).to(DEV)
+    y = _targets(B, 15, gen).to(DEV)
     logits_r, pyr_r = ref(xs)
     loss_r = torch.nn.functional.binary_cross_entropy_with_logits(logits_r, y)
     if pyramid:
@@ -108,7 +110,8 @@ def test_fusion_transformer_parity(api, precision, fusion, pyramid):
 def test_distillation_step_parity(api, precision):
     """Frozen 3-expert cross-attention teacher -> RGB-only pyramid student, BCE + CE + KL + pyramid BCE."""
     from oracle import param
-    common = dict(d=256, nhead=4, nhid=512, nlayers=2, dropout=0.0, batch_size=8, frames=16, n_classes=15)
+    B = 8 if precision == "fp32" else 48
+    common = dict(d=256, nhead=4, nhid=512, nlayers=2, dropout=0.0, batch_size=B, frames=16, n_classes=15)
     torch.manual_seed(1130)
     t_ref = param.FusionTransformer(in_dims=(2048, 1024, 128), fusion="cross", **common).to(DEV).eval()
     s_ref = param.FusionTransformer(in_dims=(2048,), fusion="sum", pyramid=True, **common).to(DEV)
@@ -116,8 +119,8 @@ def test_distillation_step_parity(api, precision):
     student = copy_state(api.FusionTransformer(in_dims=(2048,), fusion="sum", pyramid=True, precision=precision, **common), s_ref).to(DEV)
     trainer = api.DistillationTrainer(teacher, student, temperature=2.0, alpha=0.5).train()
     gen = torch.Generator().manual_seed(1130)
-    xs = [torch.randn(8, 16, D, generator=gen).to(DEV) for D in (2048, 1024, 128)]
-    y = _targets(8, 15, gen).to(DEV)
+    xs = [torch.randn(B, 16, D, generator=gen).to(DEV) for D in (2048, 1024, 128)]
+    y = _targets(B, 15, gen).to(DEV)
     with torch.no_grad():
         t_logits, _ = t_ref(xs)
     s_logits, s_pyr = s_ref(xs[:1])
@@ -139,9 +142,10 @@ def test_frame_stream_parity(api, precision):
     ref = param.FrameStream(**kw).to(DEV)
     mod = copy_state(api.FrameStream(precision=precision, **kw), ref).to(DEV)
     gen = torch.Generator().manual_seed(1130)
-    feats = torch.randn(4, 14, 896, generator=gen).to(DEV)
-    y = _targets(4, 19, gen).to(DEV)
-    teacher = torch.randn(4, 19, generator=gen).to(DEV)
+    B = 4 if precision == "fp32" else 48
+    feats = torch.randn(B, 14, 896, generator=gen).to(DEV)
+    y = _targets(B, 19, gen).to(DEV)
+    teacher = torch.randn(B, 19, generator=gen).to(DEV)
     loss_r, _ = param.distill_loss(ref(feats), teacher, y)
     loss_r.backward()
     loss = mod.training_step((y, feats), 0, teacher_logits=teacher)
