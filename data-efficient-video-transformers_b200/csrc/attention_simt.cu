@@ -230,7 +230,29 @@ int launch_bwd(const Params& p, bool f32, cudaStream_t s) {
 }  // namespace attn_simt
 }  // namespace tvt
 
+namespace tvt {
+namespace attn_tc {  // attention_sm100.cu
+bool supported(long long sq, long long sk, long long hd);
+int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s);
+int launch_bwd(const tvt_attention_bwd_args* a, cudaStream_t s);
+}  // namespace attn_tc
+}  // namespace tvt
+
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// impl 0: tcgen05 kernel when it applies (bf16, head_dim 64, short sequences), else the CUDA-core kernel.
+static int pick_impl(int impl, int dtype, long long sq, long long sk, long long hd, const char* who) {
+  const bool tc_ok = dtype == TVT_BF16 && tvt::attn_tc::supported(sq, sk, hd);
+  if (impl == 2 && !tc_ok) {
+    tvt::set_last_error("%s: impl=2 (tcgen05) needs bf16, head_dim 64, sq <= 256, sk <= 272", who);
+    return -1;
+  }
+  if (impl < 0 || impl > 2) {
+    tvt::set_last_error("%s: bad impl %d", who, impl);
+    return -1;
+  }
+  return impl == 0 ? (tc_ok ? 2 : 1) : impl;
+}
 
 extern "C" int tvt_attention_fwd(const tvt_attention_fwd_args* a, void* stream) {
   using namespace tvt;
@@ -245,8 +267,11 @@ extern "C" int tvt_attention_fwd(const tvt_attention_fwd_args* a, void* stream) 
   TVT_REQUIRE(al16(a->q) && al16(a->k) && al16(a->v) && al16(a->o), "tvt_attention_fwd: pointers must be 16-byte aligned");
   TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_attention_fwd: dropout_p must be in [0,1)");
   TVT_REQUIRE(a->batch * a->heads < (1ll << 31), "tvt_attention_fwd: batch*heads too large");
+  const int impl = pick_impl(a->impl, a->dtype, a->sq, a->sk, a->head_dim, "tvt_attention_fwd");
+  if (impl < 0) return TVT_EINVAL;
   int rc = require_sm100();
   if (rc != TVT_OK) return rc;
+  if (impl == 2) return attn_tc::launch_fwd(a, static_cast<cudaStream_t>(stream));
   attn_simt::Params p{};
   p.q = a->q; p.k = a->k; p.v = a->v; p.out = a->o; p.lse = a->lse;
   p.B = (int)a->batch; p.H = (int)a->heads; p.Sq = (int)a->sq; p.Sk = (int)a->sk; p.hd = (int)a->head_dim;
@@ -273,8 +298,11 @@ extern "C" int tvt_attention_bwd(const tvt_attention_bwd_args* a, void* stream) 
   TVT_REQUIRE(al16(a->q) && al16(a->k) && al16(a->v) && al16(a->o) && al16(a->d_o) && al16(a->dq) && al16(a->dk) && al16(a->dv),
               "tvt_attention_bwd: pointers must be 16-byte aligned");
   TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_attention_bwd: dropout_p must be in [0,1)");
+  const int impl = pick_impl(a->impl, a->dtype, a->sq, a->sk, a->head_dim, "tvt_attention_bwd");
+  if (impl < 0) return TVT_EINVAL;
   int rc = require_sm100();
   if (rc != TVT_OK) return rc;
+  if (impl == 2) return attn_tc::launch_bwd(a, static_cast<cudaStream_t>(stream));
   attn_simt::Params p{};
   p.q = a->q; p.k = a->k; p.v = a->v; p.o = a->o; p.d_o = a->d_o; p.lse = const_cast<float*>(a->lse);
   p.dq = a->dq; p.dk = a->dk; p.dv = a->dv;

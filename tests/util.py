@@ -22,10 +22,16 @@ def copy_state(dst, src):
     return dst
 
 
-def grads_close(mod, ref, tol, what="", skip=()):
-    """Every parameter gradient of `mod` matches `ref`'s within normwise tolerance."""
+def grads_close(mod, ref, tol, what="", skip=(), yard=None, slack=1.5):
+    """Every parameter gradient of `mod` matches `ref`'s within normwise tolerance `tol`.
+
+    `yard` (optional) is a copy of the fp32 oracle whose gradients were computed under stock
+    torch.autocast(bf16): a parameter may exceed `tol` only if stock PyTorch bf16 does so too, and then by at
+    most `slack` x the yardstick's own error (ReLU-gate flips and single-token CLS rows are inherently noisy
+    in bf16 for any implementation).  Returns (worst name, worst error, number of yardstick exemptions)."""
     rp = dict(ref.named_parameters())
-    worst = ("", 0.0)
+    yp = dict(yard.named_parameters()) if yard is not None else {}
+    worst, exempt = ("", 0.0), 0
     for name, p in mod.named_parameters():
         if any(s in name for s in skip):
             continue
@@ -40,5 +46,9 @@ def grads_close(mod, ref, tol, what="", skip=()):
         e = rel_err(p.grad.cpu(), g_ref.cpu())
         if e > worst[1]:
             worst = (name, e)
-        assert e <= tol, f"{what}{name}: gradient relative error {e:.3e} > {tol:.1e}"
-    return worst
+        limit = tol
+        if e > tol and name in yp and yp[name].grad is not None:
+            limit = max(tol, slack * rel_err(yp[name].grad.cpu(), g_ref.cpu()))
+            exempt += 1
+        assert e <= limit, f"{what}{name}: gradient relative error {e:.3e} > {limit:.1e}"
+    return worst[0], worst[1], exempt
