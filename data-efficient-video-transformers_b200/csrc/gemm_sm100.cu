@@ -22,7 +22,10 @@ namespace gemm {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each owning half the tile columns
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kStagePitch = 64;              // bytes per staged row: 32 bf16; 16 B chunks XOR-swizzled by (row >> 1) & 3
+constexpr int kEpiStageBytes = 32 * kStagePitch;  // per epilogue warp
 constexpr int kSmemLimit = 227 * 1024;
 
 struct Params {
@@ -38,19 +41,22 @@ struct Params {
   float* out_f32; long long ld_f32; int atomic_out;
   __nv_bfloat16* out_bf16; __nv_bfloat16* out_bf16_lo; long long ld_bf16;
   unsigned mn_lbo, mn_sbo;  // MN-major descriptor strides (bring-up knob, see tvt_debug_set_mn_desc)
+  int dbg;                  // bring-up knob: 1 = epilogue drains TMEM only, 2 = no global stores
 };
 
 static unsigned g_mn_lbo = BK * 128, g_mn_sbo = 1024;
+static int g_dbg = 0;
 
 template <int BN, int kPlanes>
 struct Cfg {
   static constexpr int kAPlane = BM * BK * 2;
   static constexpr int kBPlane = BN * BK * 2;
   static constexpr int kStageBytes = kPlanes * (kAPlane + kBPlane);
-  static constexpr int kStages = (kSmemLimit - 2048) / kStageBytes;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes;
+  static constexpr int kStages = (kSmemLimit - 2048 - kEpiBytes) / kStageBytes;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * BN;  // 512 or 256: powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(kSmemBytes <= kSmemLimit, "smem budget");
 };
@@ -75,75 +81,99 @@ __device__ __forceinline__ void store8(void* base, int is_f32, long long off, co
   }
 }
 
-// Fused epilogue on 8 consecutive columns of one output row.
-__device__ __forceinline__ void epilogue8(const Params& p, long long row, int col, float (&v)[8]) {
+// Fused epilogue on one 32-column chunk of one output row (v = raw accumulators in, final values out).
+// ng = number of valid 8-column groups in the chunk (4 except in the last column block of a ragged N).
+// Every optional stage is ONE uniform branch around a straight-line block, which keeps the epilogue small
+// enough for the instruction cache (the first version, branching per 8-column group, was I$-bound).
+__device__ __forceinline__ void epilogue32(const Params& p, long long row, int col0, int ng, float (&v)[32]) {
   if (p.atomic_out) {
-    float* dst = p.out_f32 + row * p.ld_f32 + col;
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0] * p.alpha),
-                 "f"(v[1] * p.alpha), "f"(v[2] * p.alpha), "f"(v[3] * p.alpha)
-                 : "memory");
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4] * p.alpha),
-                 "f"(v[5] * p.alpha), "f"(v[6] * p.alpha), "f"(v[7] * p.alpha)
-                 : "memory");
+    float* dst = p.out_f32 + row * p.ld_f32 + col0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < 2 * ng)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(v[4 * q] * p.alpha),
+                     "f"(v[4 * q + 1] * p.alpha), "f"(v[4 * q + 2] * p.alpha), "f"(v[4 * q + 3] * p.alpha)
+                     : "memory");
     return;
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+  for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
   if (p.bias) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < 2 * ng) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
+        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      }
   }
-  if (p.out_preact) store8(p.out_preact, p.preact_f32, row * p.ld_preact + col, v);
+  if (p.out_preact) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) store8(p.out_preact, p.preact_f32, row * p.ld_preact + col0 + 8 * g, *reinterpret_cast<float(*)[8]>(&v[8 * g]));
+  }
   if (p.act == TVT_ACT_RELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
   } else if (p.act == TVT_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_f(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
   }
   if (p.relu_mask) {
-    float m[8];
-    load8(p.relu_mask, p.mask_f32, row * p.ld_mask + col, m);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = m[i] > 0.0f ? v[i] : 0.0f;
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) {
+        float m[8];
+        load8(p.relu_mask, p.mask_f32, row * p.ld_mask + col0 + 8 * g, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * g + i] = m[i] > 0.0f ? v[8 * g + i] : 0.0f;
+      }
   }
   if (p.gelu_gate) {
-    float g[8];
-    load8(p.gelu_gate, p.gate_f32, row * p.ld_gate + col, g);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= gelu_grad_f(g[i]);
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) {
+        float m[8];
+        load8(p.gelu_gate, p.gate_f32, row * p.ld_gate + col0 + 8 * g, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * g + i] *= gelu_grad_f(m[i]);
+      }
   }
   if (p.dropout_thr16) {
-    const unsigned long long e = static_cast<unsigned long long>(row) * p.N + col;
-    const uint64_t b0 = dropout_bits4(p.dropout_seed, e >> 2);
-    const uint64_t b1 = dropout_bits4(p.dropout_seed, (e >> 2) + 1);
+    const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[i] = dropout_keep_lane(b0, i, p.dropout_thr16) ? v[i] * p.dropout_scale : 0.0f;
-      v[4 + i] = dropout_keep_lane(b1, i, p.dropout_thr16) ? v[4 + i] * p.dropout_scale : 0.0f;
+    for (int q = 0; q < 8; ++q) {
+      const uint64_t bits = dropout_bits4(p.dropout_seed, e4 + q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[4 * q + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? v[4 * q + i] * p.dropout_scale : 0.0f;
     }
   }
   if (p.residual) {
-    float r[8];
-    load8(p.residual, p.residual_f32, row * p.ld_residual + col, r);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += r[i];
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) {
+        float m[8];
+        load8(p.residual, p.residual_f32, row * p.ld_residual + col0 + 8 * g, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * g + i] += m[i];
+      }
   }
-  if (p.out_f32) store8(p.out_f32, 1, row * p.ld_f32 + col, v);
-  if (p.out_bf16) {
-    float hi[8];
+  if (p.out_f32) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) hi[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
-    Vec16<__nv_bfloat16>::store(p.out_bf16 + row * p.ld_bf16 + col, hi);
-    if (p.out_bf16_lo) {
-      float lo[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) lo[i] = v[i] - hi[i];
-      Vec16<__nv_bfloat16>::store(p.out_bf16_lo + row * p.ld_bf16 + col, lo);
-    }
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) store8(p.out_f32, 1, row * p.ld_f32 + col0 + 8 * g, *reinterpret_cast<float(*)[8]>(&v[8 * g]));
   }
+  if (p.out_bf16 && p.out_bf16_lo) {  // fp32-parity mode: hi / lo planes, written directly
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ng) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { hi[i] = __bfloat162float(__float2bfloat16_rn(v[8 * g + i])); lo[i] = v[8 * g + i] - hi[i]; }
+        Vec16<__nv_bfloat16>::store(p.out_bf16 + row * p.ld_bf16 + col0 + 8 * g, hi);
+        Vec16<__nv_bfloat16>::store(p.out_bf16_lo + row * p.ld_bf16 + col0 + 8 * g, lo);
+      }
+  }
+  // the plain bf16 output (the hot path) is staged through shared memory by the caller
 }
 
 template <int BN, bool kAMN, bool kBMN, int kPlanes>
@@ -155,7 +185,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* epi_stage = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + C::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tfull_bar = bars + 2 * C::kStages;
@@ -172,7 +203,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < C::kAccStages; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -277,7 +308,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+    const int ew = warp - 4;
+    const int quad = ew & 3;     // == warp % 4: the TMEM lane quadrant this warp may read
+    const int half = ew >> 2;    // which half of the tile's columns this warp drains
+    const uint32_t stage_addr = smem_u32(epi_stage + ew * kEpiStageBytes);
+    const bool staged = p.out_bf16 != nullptr && p.out_bf16_lo == nullptr && !p.atomic_out;
     int as = 0;
     uint32_t aphase = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -288,26 +323,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
-      const long long row = static_cast<long long>(m_blk) * BM + ew * 32 + lane;
+      const long long row0 = static_cast<long long>(m_blk) * BM + quad * 32;
+      const long long row = row0 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n_blk * BN + c * 32;
+      for (int c = 0; c < BN / 64; ++c) {
+        const int tcol = half * (BN / 2) + c * 32;   // column inside the tile
+        const int col0 = n_blk * BN + tcol;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, r);
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + tcol, r);
         tmem_ld_wait();
-        if (row_ok) {
+        if (p.dbg == 1) continue;
+        float v[32];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              float v[8];
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const int ng = (p.N - col0) >= 32 ? 4 : (p.N - col0) >> 3;
+        if (row_ok) epilogue32(p, row, col0, ng, v);
+        if (staged) {
+          // thread == row: four 16 B chunks, XOR-swizzled so neither this write nor the read-back below conflicts
+          const uint32_t wbase = stage_addr + lane * kStagePitch;
+          const int sw = (lane >> 1) & 3;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              epilogue8(p, row, col, v);
-            }
+          for (int g = 0; g < 4; ++g)
+            sts128(wbase + ((g ^ sw) << 4), pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                   pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+          __syncwarp();
+          // coalesced write-out: 4 lanes x 16 B cover one staged row (64 B), 8 rows per pass
+          const int seg = lane & 3;
+          const int gcol = col0 + seg * 8;
+          __nv_bfloat16* gptr = p.out_bf16 + (row0 + (lane >> 2)) * p.ld_bf16 + gcol;
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int rr = ps * 8 + (lane >> 2);
+            const uint4 val = lds128(stage_addr + rr * kStagePitch + ((seg ^ ((rr >> 1) & 3)) << 4));
+            if (row0 + rr < p.M && gcol < p.N && kb1 > kb0 && p.dbg != 2) *reinterpret_cast<uint4*>(gptr + static_cast<long long>(ps) * 8 * p.ld_bf16) = val;
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -419,6 +471,8 @@ extern "C" void tvt_debug_set_mn_desc(unsigned lbo, unsigned sbo) {
   tvt::gemm::g_mn_sbo = sbo;
 }
 
+extern "C" void tvt_debug_set_epilogue(int mode) { tvt::gemm::g_dbg = mode; }
+
 extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   using namespace tvt;
   TVT_REQUIRE(a != nullptr, "tvt_gemm: null args");
@@ -476,7 +530,7 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32; p.atomic_out = a->atomic_out;
   p.out_bf16 = (__nv_bfloat16*)a->out_bf16; p.out_bf16_lo = (__nv_bfloat16*)a->out_bf16_lo; p.ld_bf16 = a->ld_bf16;
 
-  p.mn_lbo = gemm::g_mn_lbo; p.mn_sbo = gemm::g_mn_sbo;
+  p.mn_lbo = gemm::g_mn_lbo; p.mn_sbo = gemm::g_mn_sbo; p.dbg = gemm::g_dbg;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // Tile width: 256 columns unless that leaves most SMs idle.

@@ -12,6 +12,7 @@
 #include "../include/tvt.h"
 
 extern "C" void tvt_debug_set_mn_desc(unsigned lbo, unsigned sbo);
+extern "C" void tvt_debug_set_epilogue(int mode);
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
@@ -103,6 +104,12 @@ static void bench(int M, int N, int K, int amn, int bmn, int planes, int splits)
 
 int main(int argc, char** argv) {
   if (tvt_device_check() != 0) { printf("device check failed: %s\n", tvt_last_error()); return 1; }
+  if (getenv("TVT_EPI_DBG")) tvt_debug_set_epilogue(atoi(getenv("TVT_EPI_DBG")));
+  if (argc >= 5 && !strcmp(argv[1], "one")) {   // gemm_check one M N K [amn bmn planes splits]: a single shape, for ncu
+    bench(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 0, argc > 6 ? atoi(argv[6]) : 0,
+          argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 1);
+    return 0;
+  }
   int fails = 0;
   // K-major / K-major first (the forward product)
   Case kk[] = {{128, 128, 64, 0, 0, 1, 1, 0}, {128, 256, 128, 0, 0, 1, 1, 0}, {256, 512, 512, 0, 0, 1, 1, 0}, {200, 264, 200, 0, 0, 1, 1, 1},
