@@ -85,7 +85,8 @@ __device__ __forceinline__ void store8(void* base, int is_f32, long long off, co
 // ng = number of valid 8-column groups in the chunk (4 except in the last column block of a ragged N).
 // Every optional stage is ONE uniform branch around a straight-line block, which keeps the epilogue small
 // enough for the instruction cache (the first version, branching per 8-column group, was I$-bound).
-__device__ __forceinline__ void epilogue32(const Params& p, long long row, int col0, int ng, float (&v)[32]) {
+__device__ __forceinline__ void epilogue32(const Params& p, long long row, int col0, int ng, float (&v)[32],
+                                           const uint32_t (&mask_pk)[16], const uint32_t (&res_pk)[16], bool pre) {
   if (p.atomic_out) {
     float* dst = p.out_f32 + row * p.ld_f32 + col0;
 #pragma unroll
@@ -119,14 +120,23 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
     for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
   }
   if (p.relu_mask) {
+    if (pre && !p.mask_f32) {   // bf16 mask row fetched coalesced by the caller: sign/zero test on the raw halves
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (g < ng) {
-        float m[8];
-        load8(p.relu_mask, p.mask_f32, row * p.ld_mask + col0 + 8 * g, m);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[8 * g + i] = m[i] > 0.0f ? v[8 * g + i] : 0.0f;
+      for (int i = 0; i < 16; ++i) {
+        const float2 m = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mask_pk[i]));
+        v[2 * i] = m.x > 0.0f ? v[2 * i] : 0.0f;
+        v[2 * i + 1] = m.y > 0.0f ? v[2 * i + 1] : 0.0f;
       }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g < ng) {
+          float m[8];
+          load8(p.relu_mask, p.mask_f32, row * p.ld_mask + col0 + 8 * g, m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[8 * g + i] = m[i] > 0.0f ? v[8 * g + i] : 0.0f;
+        }
+    }
   }
   if (p.gelu_gate) {
 #pragma unroll
@@ -148,14 +158,23 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
     }
   }
   if (p.residual) {
+    if (pre && !p.residual_f32) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (g < ng) {
-        float m[8];
-        load8(p.residual, p.residual_f32, row * p.ld_residual + col0 + 8 * g, m);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[8 * g + i] += m[i];
+      for (int i = 0; i < 16; ++i) {
+        const float2 m = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&res_pk[i]));
+        v[2 * i] += m.x;
+        v[2 * i + 1] += m.y;
       }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g < ng) {
+          float m[8];
+          load8(p.residual, p.residual_f32, row * p.ld_residual + col0 + 8 * g, m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[8 * g + i] += m[i];
+        }
+    }
   }
   if (p.out_f32) {
 #pragma unroll
@@ -174,6 +193,36 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
       }
   }
   // the plain bf16 output (the hot path) is staged through shared memory by the caller
+}
+
+// Warp-cooperative fetch of a [32 rows x 32 bf16] block of a row-major matrix: global reads are coalesced
+// (4 lanes x 16 B per row, 8 rows per pass), the block is transposed to "one row per lane" through the
+// warp's swizzled staging buffer.  Rows >= M / columns >= N read as zero.
+__device__ __forceinline__ void fetch_rows32(const void* base, long long ld, long long row0, int col0, int M, int N,
+                                             uint32_t stage_addr, int lane, uint32_t (&out)[16]) {
+  const int seg = lane & 3;
+  const int gcol = col0 + seg * 8;
+  const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(base) + (row0 + (lane >> 2)) * ld + gcol;
+  uint4 t[4];
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int rr = ps * 8 + (lane >> 2);
+    t[ps] = make_uint4(0, 0, 0, 0);
+    if (row0 + rr < M && gcol < N) t[ps] = __ldg(reinterpret_cast<const uint4*>(gptr + static_cast<long long>(ps) * 8 * ld));
+  }
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int rr = ps * 8 + (lane >> 2);
+    sts128(stage_addr + rr * kStagePitch + ((seg ^ ((rr >> 1) & 3)) << 4), t[ps].x, t[ps].y, t[ps].z, t[ps].w);
+  }
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 q = lds128(stage_addr + lane * kStagePitch + ((g ^ sw) << 4));
+    out[4 * g] = q.x; out[4 * g + 1] = q.y; out[4 * g + 2] = q.z; out[4 * g + 3] = q.w;
+  }
+  __syncwarp();
 }
 
 template <int BN, bool kAMN, bool kBMN, int kPlanes>
@@ -331,6 +380,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int tcol = half * (BN / 2) + c * 32;   // column inside the tile
         const int col0 = n_blk * BN + tcol;
         if (col0 >= p.N) break;  // warp-uniform
+        // operands of the fused stages that live in global memory: fetched coalesced, one warp = 32 rows
+        uint32_t mask_pk[16], res_pk[16];
+        const bool pre = !p.atomic_out;
+        if (pre && p.relu_mask && !p.mask_f32) fetch_rows32(p.relu_mask, p.ld_mask, row0, col0, p.M, p.N, stage_addr, lane, mask_pk);
+        if (pre && p.residual && !p.residual_f32) fetch_rows32(p.residual, p.ld_residual, row0, col0, p.M, p.N, stage_addr, lane, res_pk);
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + tcol, r);
         tmem_ld_wait();
@@ -339,7 +393,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
         const int ng = (p.N - col0) >= 32 ? 4 : (p.N - col0) >> 3;
-        if (row_ok) epilogue32(p, row, col0, ng, v);
+        if (row_ok) epilogue32(p, row, col0, ng, v, mask_pk, res_pk, pre);
         if (staged) {
           // thread == row: four 16 B chunks, XOR-swizzled so neither this write nor the read-back below conflicts
           const uint32_t wbase = stage_addr + lane * kStagePitch;
@@ -533,9 +587,16 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   p.mn_lbo = gemm::g_mn_lbo; p.mn_sbo = gemm::g_mn_sbo; p.dbg = gemm::g_dbg;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // Tile width: 256 columns unless that leaves most SMs idle.
-  const long long tiles256 = ((a->m + 127) / 128) * ((a->n + 255) / 256) * a->splits;
-  const bool narrow = a->n <= 128 || tiles256 < tvt::num_sms();
+  // Tile width by a small cost model (cycles): waves x (k-blocks x MMA time per k-block + epilogue).  128-wide
+  // tiles double the CTA count but run the main loop at the shared-memory bandwidth limit (A and B tiles are
+  // the same size), so they only win when 256-wide tiles would leave SMs idle on a short-K problem.
+  const long long nsm = tvt::num_sms();
+  const long long m_tiles = (a->m + 127) / 128;
+  const long long kb_per = (kb_total + a->splits - 1) / a->splits;
+  const long long w256 = m_tiles * ((a->n + 255) / 256) * a->splits, w128 = m_tiles * ((a->n + 127) / 128) * a->splits;
+  const long long c256 = ((w256 + nsm - 1) / nsm) * (kb_per * 512 + 3000);
+  const long long c128 = ((w128 + nsm - 1) / nsm) * (kb_per * 400 + 1800);
+  const bool narrow = a->n <= 128 || c128 < c256;
   if (a->a_lo) return narrow ? gemm::dispatch_major<128, 2>(a, p, s) : gemm::dispatch_major<256, 2>(a, p, s);
   return narrow ? gemm::dispatch_major<128, 1>(a, p, s) : gemm::dispatch_major<256, 1>(a, p, s);
 }

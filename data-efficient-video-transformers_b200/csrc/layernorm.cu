@@ -28,25 +28,61 @@ __global__ void __launch_bounds__(kWarps * 32) ln_fwd_kernel(const FwdParams p) 
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * kWarps;
-  for (long long row = warp0; row < p.rows; row += nwarps) {
-    const T* src;
-    const float* pe_row = nullptr;
+  // each lane always owns the same columns: keep their gamma / beta in registers for every row
+  float gam[kChunks][V], bet[kChunks][V];
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int col = (c * 32 + lane) * V;
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+      if (col < p.d) {
+        g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + i));
+        b4 = __ldg(reinterpret_cast<const float4*>(p.beta + col + i));
+      }
+      gam[c][i] = g4.x; gam[c][i + 1] = g4.y; gam[c][i + 2] = g4.z; gam[c][i + 3] = g4.w;
+      bet[c][i] = b4.x; bet[c][i + 1] = b4.y; bet[c][i + 2] = b4.z; bet[c][i + 3] = b4.w;
+    }
+  }
+  auto src_of = [&](long long row, const float*& pe_row) -> const T* {
     if (p.S > 0) {
       const long long b = row / p.S;
       const int s = static_cast<int>(row - b * p.S);
-      src = s == 0 ? reinterpret_cast<const T*>(p.cls) + b * p.d
-                   : reinterpret_cast<const T*>(p.x) + (b * (p.S - 1) + (s - 1)) * p.d;
       pe_row = p.pe + static_cast<long long>(s) * p.d;
-    } else {
-      src = reinterpret_cast<const T*>(p.x) + row * p.d;
+      return s == 0 ? reinterpret_cast<const T*>(p.cls) + b * p.d
+                    : reinterpret_cast<const T*>(p.x) + (b * (p.S - 1) + (s - 1)) * p.d;
+    }
+    pe_row = nullptr;
+    return reinterpret_cast<const T*>(p.x) + row * p.d;
+  };
+  uint4 raw[kChunks], nxt[kChunks];
+  const float* pe_row = nullptr;
+  if (warp0 < p.rows) {
+    const T* src = src_of(warp0, pe_row);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      raw[c] = col < p.d ? ldg_stream(src + col) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (long long row = warp0; row < p.rows; row += nwarps) {
+    // software pipeline: the next row's 16-byte loads are in flight while this row is reduced
+    const float* pe_next = nullptr;
+    if (row + nwarps < p.rows) {
+      const T* src = src_of(row + nwarps, pe_next);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = (c * 32 + lane) * V;
+        nxt[c] = col < p.d ? ldg_stream(src + col) : make_uint4(0, 0, 0, 0);
+      }
     }
     float v[kChunks][V];
     float sum = 0.0f;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
       const int col = (c * 32 + lane) * V;
+      Vec16<T>::unpack(raw[c], v[c]);
       if (col < p.d) {
-        Vec16<T>::load(src + col, v[c]);
         if (pe_row) {
 #pragma unroll
           for (int i = 0; i < V; ++i) v[c][i] += pe_row[col + i];
@@ -60,9 +96,6 @@ __global__ void __launch_bounds__(kWarps * 32) ln_fwd_kernel(const FwdParams p) 
         }
 #pragma unroll
         for (int i = 0; i < V; ++i) sum += v[c][i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < V; ++i) v[c][i] = 0.0f;
       }
     }
     const float mean = warp_sum(sum) / p.d;
@@ -87,10 +120,13 @@ __global__ void __launch_bounds__(kWarps * 32) ln_fwd_kernel(const FwdParams p) 
       if (col < p.d) {
         float o[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = (v[c][i] - mean) * rstd * __ldg(p.gamma + col + i) + __ldg(p.beta + col + i);
+        for (int i = 0; i < V; ++i) o[i] = (v[c][i] - mean) * rstd * gam[c][i] + bet[c][i];
         Vec16<T>::store(dst + col, o);
       }
     }
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) raw[c] = nxt[c];
+    pe_row = pe_next;
   }
 }
 
@@ -109,22 +145,53 @@ struct BwdParams {
   long long dropout_ld;  // row pitch used for dropout element indices (N of the producing GEMM)
 };
 
+constexpr int kBwdWarps = 4;
+
 template <typename T, int kChunks>
-__global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kBwdWarps * 32) ln_bwd_kernel(const BwdParams p) {
   constexpr int V = Vec16<T>::kN;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const long long warp0 = static_cast<long long>(blockIdx.x) * kWarps + warp;
-  const long long nwarps = static_cast<long long>(gridDim.x) * kWarps;
-  float acc_g[kChunks][V], acc_b[kChunks][V], acc_z[kChunks][V];
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kBwdWarps;
+  float acc_g[kChunks][V], acc_b[kChunks][V], acc_z[kChunks][V], gam[kChunks][V];
 #pragma unroll
-  for (int c = 0; c < kChunks; ++c)
+  for (int c = 0; c < kChunks; ++c) {
+    const int col = (c * 32 + lane) * V;
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < p.d) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + i));
+      gam[c][i] = g4.x; gam[c][i + 1] = g4.y; gam[c][i + 2] = g4.z; gam[c][i + 3] = g4.w;
+    }
 #pragma unroll
     for (int i = 0; i < V; ++i) acc_g[c][i] = acc_b[c][i] = acc_z[c][i] = 0.0f;
+  }
 
+  uint4 rdy[kChunks], rx[kChunks], ndy[kChunks], nx[kChunks];
+  if (warp0 < p.rows) {
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      rdy[c] = rx[c] = make_uint4(0, 0, 0, 0);
+      if (col < p.d) {
+        rdy[c] = ldg_stream(reinterpret_cast<const T*>(p.dy) + warp0 * p.d + col);
+        rx[c] = ldg_stream(reinterpret_cast<const T*>(p.x) + warp0 * p.d + col);
+      }
+    }
+  }
   for (long long row = warp0; row < p.rows; row += nwarps) {
-    const T* dy = reinterpret_cast<const T*>(p.dy) + row * p.d;
-    const T* x = reinterpret_cast<const T*>(p.x) + row * p.d;
+    if (row + nwarps < p.rows) {   // next row's loads in flight while this row is processed
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = (c * 32 + lane) * V;
+        ndy[c] = nx[c] = make_uint4(0, 0, 0, 0);
+        if (col < p.d) {
+          ndy[c] = ldg_stream(reinterpret_cast<const T*>(p.dy) + (row + nwarps) * p.d + col);
+          nx[c] = ldg_stream(reinterpret_cast<const T*>(p.x) + (row + nwarps) * p.d + col);
+        }
+      }
+    }
     const float mean = p.mean[row], rstd = p.rstd[row];
     float g[kChunks][V], xh[kChunks][V];
     float s1 = 0.0f, s2 = 0.0f;
@@ -133,14 +200,14 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const BwdParams p) 
       const int col = (c * 32 + lane) * V;
       if (col < p.d) {
         float dyv[V], xv[V];
-        Vec16<T>::load(dy + col, dyv);
-        Vec16<T>::load(x + col, xv);
+        Vec16<T>::unpack(rdy[c], dyv);
+        Vec16<T>::unpack(rx[c], xv);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           xh[c][i] = (xv[i] - mean) * rstd;
           acc_g[c][i] += dyv[i] * xh[c][i];
           acc_b[c][i] += dyv[i];
-          g[c][i] = dyv[i] * __ldg(p.gamma + col + i);
+          g[c][i] = dyv[i] * gam[c][i];
           s1 += g[c][i];
           s2 += g[c][i] * xh[c][i];
         }
@@ -179,9 +246,11 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const BwdParams p) 
         for (int i = 0; i < V; ++i) acc_z[c][i] += o[i];
       }
     }
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) { rdy[c] = ndy[c]; rx[c] = nx[c]; }
   }
   // CTA-level reduction of the column partials through shared memory, then one atomic per column.
-  __shared__ float red[kWarps][32 * V + 1];
+  __shared__ float red[kBwdWarps][32 * V + 1];
   for (int which = 0; which < 3; ++which) {
     float* out = which == 0 ? p.dgamma : (which == 1 ? p.dbeta : p.dbias);
     if (!out) continue;  // uniform
@@ -192,10 +261,10 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const BwdParams p) 
       for (int i = 0; i < V; ++i)
         red[warp][lane * V + i] = which == 0 ? acc_g[c][i] : (which == 1 ? acc_b[c][i] : acc_z[c][i]);
       __syncthreads();
-      for (int t = threadIdx.x; t < 32 * V; t += kWarps * 32) {
+      for (int t = threadIdx.x; t < 32 * V; t += kBwdWarps * 32) {
         float s = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += red[w][t];
+        for (int w = 0; w < kBwdWarps; ++w) s += red[w][t];
         const int col = c * 32 * V + t;
         if (col < p.d) atomicAdd(out + col, s);
       }
@@ -235,10 +304,10 @@ template <typename T, int C>
 struct BwdLauncher {
   static int run(const BwdParams& p, cudaStream_t s) {
     // fewer, fatter CTAs: each ends with d atomics per output vector
-    const long long want = (p.rows + kWarps * 4 - 1) / (kWarps * 4);
-    const long long cap = static_cast<long long>(num_sms()) * 2;
+    const long long want = (p.rows + kBwdWarps * 4 - 1) / (kBwdWarps * 4);
+    const long long cap = static_cast<long long>(num_sms()) * 3;
     const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
-    ln_bwd_kernel<T, C><<<grid, kWarps * 32, 0, s>>>(p);
+    ln_bwd_kernel<T, C><<<grid, kBwdWarps * 32, 0, s>>>(p);
     return check_launch("tvt_layernorm_bwd");
   }
 };
@@ -254,7 +323,7 @@ extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) 
   TVT_REQUIRE(a->x && a->y && a->gamma && a->beta, "tvt_layernorm_fwd: null pointer");
   TVT_REQUIRE(a->rows >= 0 && a->d > 0 && a->d % 8 == 0, "tvt_layernorm_fwd: d must be a positive multiple of 8 (got %lld)", (long long)a->d);
   TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_layernorm_fwd: bad dtype");
-  TVT_REQUIRE(al16(a->x) && al16(a->y) && al16(a->cls) && al16(a->pre), "tvt_layernorm_fwd: pointers must be 16-byte aligned");
+  TVT_REQUIRE(al16(a->x) && al16(a->y) && al16(a->cls) && al16(a->pre) && al16(a->gamma) && al16(a->beta), "tvt_layernorm_fwd: pointers must be 16-byte aligned");
   TVT_REQUIRE(a->seq_len >= 0, "tvt_layernorm_fwd: bad seq_len");
   if (a->seq_len > 0) {
     TVT_REQUIRE(a->cls && a->pe, "tvt_layernorm_fwd: embed mode needs cls and pe");
@@ -284,7 +353,7 @@ extern "C" int tvt_layernorm_bwd(const tvt_layernorm_bwd_args* a, void* stream) 
   TVT_REQUIRE(a->dy && a->x && a->mean && a->rstd && a->gamma, "tvt_layernorm_bwd: null pointer");
   TVT_REQUIRE(a->rows >= 0 && a->d > 0 && a->d % 8 == 0, "tvt_layernorm_bwd: d must be a positive multiple of 8");
   TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_layernorm_bwd: bad dtype");
-  TVT_REQUIRE(al16(a->dy) && al16(a->x) && al16(a->dx) && al16(a->dz) && al16(a->dfeat) && al16(a->dcls),
+  TVT_REQUIRE(al16(a->dy) && al16(a->x) && al16(a->dx) && al16(a->dz) && al16(a->dfeat) && al16(a->dcls) && al16(a->gamma),
               "tvt_layernorm_bwd: pointers must be 16-byte aligned");
   if (a->seq_len > 0) {
     TVT_REQUIRE(a->seq_len >= 2 && a->rows % a->seq_len == 0, "tvt_layernorm_bwd: rows must be a multiple of seq_len");

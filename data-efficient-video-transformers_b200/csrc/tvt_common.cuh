@@ -53,6 +53,9 @@ struct Vec16<float> {
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
 };
 template <>
 struct Vec16<__nv_bfloat16> {
@@ -73,7 +76,22 @@ struct Vec16<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = t;
   }
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
 };
+
+// 16-byte streaming load that bypasses L1 allocation (each element of these kernels is read exactly once).
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

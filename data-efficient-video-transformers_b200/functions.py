@@ -235,7 +235,7 @@ class MlpFn(torch.autograd.Function):
             if tiles * 4 <= ops.num_sms() and kb >= 16:
                 wh, wl = mode.weight(ws[i])
                 acc = torch.zeros(M, N, dtype=torch.float32, device=x.device)
-                splits = max(1, min(kb, ops.num_sms() // tiles))
+                splits = max(2, ops.pick_splits(((M + 127) // 128) * ((N + 255) // 256), kb, 64))
                 ops.gemm(curp[0], wh, M, N, K, a_lo=curp[1], b_lo=wl, out_f32=acc, splits=splits, atomic=True)
                 if z is not None:
                     ops.bias_act(acc, bs[i], z, ACT_NONE)

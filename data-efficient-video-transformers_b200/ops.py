@@ -117,6 +117,19 @@ def act_bwd(dy, y_or_z, act, dropout_p=0.0, seed=0):
     return dx
 
 
+def pick_splits(tiles, k_blocks, max_splits=32):
+    """Split-K factor for a GEMM with few output tiles and a long contraction (wgrad, skinny MLP layers):
+    minimise  waves x (k-blocks per split x 512 cycles + 4000 cycles of atomic epilogue)."""
+    nsm = num_sms()
+    best, best_cost = 1, None
+    for s in range(1, max(1, min(max_splits, k_blocks)) + 1):
+        waves = -(-tiles * s // nsm)
+        cost = waves * (-(-k_blocks // s) * 512 + (4000 if s > 1 else 3000))
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s, cost
+    return best
+
+
 class Mode:
     """Precision mode + per-step cache of bf16 weight planes (keyed on the parameter's version counter)."""
 
@@ -187,9 +200,7 @@ class Mode:
 
     # dW[N,K] = dy[M,N]^T x[M,K]  (fp32, split-K over the token dimension when the tile grid is small)
     def wgrad(self, dyp, xp, M, N, K, out=None):
-        tiles = ((N + 127) // 128) * ((K + 255) // 256)
-        kb = (M + 63) // 64
-        splits = max(1, min(kb, num_sms() // max(tiles, 1)))
+        splits = pick_splits(((N + 127) // 128) * ((K + 255) // 256), (M + 63) // 64)
         if out is None:
             out = (torch.zeros if splits > 1 else torch.empty)(N, K, dtype=torch.float32, device=dyp[0].device)
         elif splits > 1:

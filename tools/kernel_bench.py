@@ -94,7 +94,8 @@ gemm_case("gemm fwd ffn1+relu+drop 33024x3072x768", n, ff, d, relu=True)
 gemm_case("gemm fwd ffn2+res 33024x768x3072", n, d, ff, fused=True)
 gemm_case("gemm dgrad ffn2   33024x3072x768", n, ff, d, b_mn=True)
 gemm_case("gemm dgrad ffn1   33024x768x3072", n, d, ff, b_mn=True)
-gemm_case("gemm wgrad ffn1   3072x768x33024", ff, d, n, a_mn=True, b_mn=True, splits=2)
-gemm_case("gemm wgrad qkv    2304x768x33024", 3 * d, d, n, a_mn=True, b_mn=True, splits=2)
-gemm_case("gemm wgrad out    768x768x33024", d, d, n, a_mn=True, b_mn=True, splits=8)
+gemm_case("gemm wgrad ffn1   3072x768x33024", ff, d, n, a_mn=True, b_mn=True, splits=ops.pick_splits(24 * 3, 516))
+gemm_case("gemm wgrad qkv    2304x768x33024", 3 * d, d, n, a_mn=True, b_mn=True, splits=ops.pick_splits(18 * 3, 516))
+gemm_case("gemm wgrad ffn2   768x3072x33024", d, ff, n, a_mn=True, b_mn=True, splits=ops.pick_splits(6 * 12, 516))
+gemm_case("gemm wgrad out    768x768x33024", d, d, n, a_mn=True, b_mn=True, splits=ops.pick_splits(6 * 3, 516))
 gemm_case("gemm inproj rgb   32768x768x2048", B * 128, d, 2048)
