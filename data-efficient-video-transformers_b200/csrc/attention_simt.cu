@@ -44,11 +44,11 @@ __device__ __forceinline__ float dot_row(const float* a, const float* b, int hd)
   return acc;
 }
 
-// Dropout on attention probabilities: element index ((b*H + h)*Sq + i)*Sk + j.
+// Dropout on attention probabilities (mask layout: tvt_common.cuh, attn_drop_bits).
 __device__ __forceinline__ float drop_mul(const Params& p, long long bh, int i, int j) {
   if (!p.dropout_thr16) return 1.0f;
-  const unsigned long long e = (static_cast<unsigned long long>(bh) * p.Sq + i) * p.Sk + j;
-  return dropout_keep(p.dropout_seed, e, p.dropout_thr16) ? p.dropout_scale : 0.0f;
+  const uint64_t bits = attn_drop_bits(p.dropout_seed, attn_rowkey(bh, p.Sq, p.Sk, i), j >> 2);
+  return dropout_keep_lane(bits, j & 3, p.dropout_thr16) ? p.dropout_scale : 0.0f;
 }
 
 template <typename T>

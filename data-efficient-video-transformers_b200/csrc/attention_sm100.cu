@@ -24,12 +24,15 @@ namespace tvt {
 namespace attn_tc {
 
 constexpr int HD = 64;        // head dim: one 128-byte swizzle atom
-constexpr int kThreads = 160;  // warps 0-3: one row per thread; warp 4: TMA / MMA issue
+constexpr int kThreads = 160;     // backward: warps 0-3 one row per thread; warp 4 TMA / MMA issue
+constexpr int kThreadsFwd = 192;  // forward: + warp 5 for the tail query rows
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct Params {
   int B, H, Sq, Sk;
   int sk_pad;                 // Sk rounded up to 16
+  int kv_box;                 // rows per K / V TMA box (divides sk_pad)
+  const __nv_bfloat16* q_in; long long ldq;   // raw Q rows for the CUDA-core tail path
   float scale;
   float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
   __nv_bfloat16* o; long long ldo;
@@ -46,8 +49,17 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
 
 __device__ __forceinline__ float drop_mul(const Params& p, long long bh, int i, int j) {
   if (!p.dropout_thr16) return 1.0f;
-  const unsigned long long e = (static_cast<unsigned long long>(bh) * p.Sq + i) * p.Sk + j;
-  return dropout_keep(p.dropout_seed, e, p.dropout_thr16) ? p.dropout_scale : 0.0f;
+  const uint64_t bits = attn_drop_bits(p.dropout_seed, attn_rowkey(bh, p.Sq, p.Sk, i), j >> 2);
+  return dropout_keep_lane(bits, j & 3, p.dropout_thr16) ? p.dropout_scale : 0.0f;
+}
+// Dropout multipliers of 16 consecutive keys [c0, c0 + 16) of one query row (c0 % 16 == 0): 4 hashes.
+__device__ __forceinline__ void drop_mul16(const Params& p, uint64_t rowkey, int c0, float (&m)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint64_t bits = attn_drop_bits(p.dropout_seed, rowkey, (c0 >> 2) + g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[4 * g + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? p.dropout_scale : 0.0f;
+  }
 }
 
 // Issue D[tmem] = A(K-major tile, 128 rows) * B(K-major tile, n rows)^T over the 64-wide contraction.
@@ -60,9 +72,25 @@ __device__ __forceinline__ void mma_kk(uint32_t d_tmem, uint32_t a_smem, uint32_
 
 // ------------------------------------------------------------------------------------------- forward
 // Warps 0-3: one query row per thread (TMEM lane == thread).  Warp 4, lane 0: issues every TMA and MMA.
-// smem: Q tile 16 KB | K sk_pad*128 | V sk_pad*128 | P ceil(sk_pad/64)*16 KB | barriers
-__global__ void __launch_bounds__(kThreads) fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                                                       const __grid_constant__ CUtensorMap tmV, const Params p) {
+// Warp 5: "tail" query rows on CUDA cores.  The sequences are 2^k + 1 tokens long, so a second 128-row
+// MMA tile would hold a single valid row (S = 129); instead the <= kMaxTail rows beyond the last full
+// tile are computed by warp 5 straight from the K / V tiles in shared memory while the tensor cores
+// work on the main tile.
+// smem: Q tile 16 KB | K sk_pad*128 | V sk_pad*128 | P ceil(sk_pad/64)*16 KB | barriers | tail scratch
+constexpr int kMaxTail = 8;
+
+__device__ __forceinline__ int main_tiles(int sq) {   // number of 128-row tensor-core tiles
+  const int full = sq / 128, rem = sq - full * 128;
+  return (full >= 1 && rem <= kMaxTail) ? full : (sq + 127) / 128;
+}
+
+// bf16 element (row, col) of a [rows x 64] 128B-swizzled tile
+__device__ __forceinline__ const __nv_bfloat16* sw_elem(const uint8_t* tile, int row, int col) {
+  return reinterpret_cast<const __nv_bfloat16*>(tile + sw128(row, col >> 3)) + (col & 7);
+}
+
+__global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                          const __grid_constant__ CUtensorMap tmV, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int kv_bytes = p.sk_pad * 128;
@@ -77,12 +105,15 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const __grid_constant__ C
   uint64_t* bar_s = bars + 2;   // S = Q K^T complete (one phase per m-tile)
   uint64_t* bar_o = bars + 3;   // O = P V complete   (one phase per m-tile)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* tail_q = reinterpret_cast<float*>(bars + 6);   // [64]
+  float* tail_p = tail_q + HD;                          // [sk_pad]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool issuer = warp == 4 && lane == 0;
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int o_col = (p.sk_pad + 63) & ~63;           // O accumulator starts on a 64-column boundary
   const uint32_t tmem_cols = o_col + HD <= 128 ? 128u : (o_col + HD <= 256 ? 256u : 512u);
+  const int m_tiles = main_tiles(p.Sq);
 
   if (issuer) {
     mbar_init(smem_u32(bar_kv), 1);
@@ -101,21 +132,70 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;                 // [128 x sk_pad] fp32
   const uint32_t tmem_O = tmem_base + o_col;         // [128 x 64] fp32
+  const float sl2 = p.scale * kLog2e;
 
   if (issuer) {
     mbar_arrive_expect_tx(smem_u32(bar_kv), 2 * kv_bytes);
-    for (int r = 0; r < p.sk_pad; r += 16) {
+    for (int r = 0; r < p.sk_pad; r += p.kv_box) {
       tma_load_2d(smem_u32(sK + r * 128), &tmK, smem_u32(bar_kv), h * HD, b * p.Sk + r);
       tma_load_2d(smem_u32(sV + r * 128), &tmV, smem_u32(bar_kv), h * HD, b * p.Sk + r);
     }
   }
-  const int m_tiles = (p.Sq + 127) / 128;
+
+  if (warp == 5) {
+    // ---- tail query rows [128 * m_tiles, Sq): scores, softmax and P V on CUDA cores
+    const int t0 = m_tiles * 128;
+    if (t0 < p.Sq) {
+      mbar_wait(smem_u32(bar_kv), 0);
+      for (int row = t0; row < p.Sq; ++row) {
+        const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + row) * p.ldq + h * HD;
+        const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qrow + 2 * lane));
+        tail_q[2 * lane] = q2.x;
+        tail_q[2 * lane + 1] = q2.y;
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < p.Sk; j += 32) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float kf[8];
+            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(j, c)), kf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc += tail_q[c * 8 + i] * kf[i];
+          }
+          tail_p[j] = acc;
+          mx = fmaxf(mx, acc);
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j < p.Sk; j += 32) {
+          const float e = exp2f((tail_p[j] - mx) * sl2);
+          sum += e;
+          tail_p[j] = e * drop_mul(p, bh, row, j);
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        float o0 = 0.0f, o1 = 0.0f;
+        for (int j = 0; j < p.Sk; ++j) {
+          const float pj = tail_p[j];
+          const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sw_elem(sV, j, 2 * lane)));
+          o0 += pj * v2.x;
+          o1 += pj * v2.y;
+        }
+        const float inv = 1.0f / sum;
+        __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + row) * p.ldo + h * HD;
+        *reinterpret_cast<__nv_bfloat162*>(orow + 2 * lane) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+        if (lane == 0 && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + row] = mx * p.scale + __logf(sum);
+        __syncwarp();
+      }
+    }
+  }
+
   uint32_t phase = 0;
-  const float sl2 = p.scale * kLog2e;
   for (int mt = 0; mt < m_tiles; ++mt, phase ^= 1) {
     if (issuer) {
       mbar_arrive_expect_tx(smem_u32(bar_q), 128 * 128);
-      for (int r = 0; r < 128; r += 16) tma_load_2d(smem_u32(sQ + r * 128), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq + mt * 128 + r);
+      tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq + mt * 128);
       if (mt == 0) mbar_wait(smem_u32(bar_kv), 0);
       mbar_wait(smem_u32(bar_q), phase);
       tc_fence_after();
@@ -133,7 +213,22 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const __grid_constant__ C
     if (warp_ok) {
       mbar_wait(smem_u32(bar_s), phase);
       tc_fence_after();
-      for (int c0 = 0; c0 < p.sk_pad; c0 += 16) {
+      // pass 1: row maximum (32 columns per TMEM load, 16 for the ragged end)
+      int c0 = 0;
+      for (; c0 + 32 <= p.sk_pad; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_S + lane_addr + c0, r);
+        tmem_ld_wait();
+        if (c0 + 32 <= p.Sk) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < p.Sk) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      if (c0 < p.sk_pad) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_S + lane_addr + c0, r);
         tmem_ld_wait();
@@ -142,24 +237,40 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const __grid_constant__ C
           if (c0 + i < p.Sk) mx = fmaxf(mx, __uint_as_float(r[i]));
       }
       const float mxs = mx * sl2;
-      const int drow = row_ok ? row : 0;
-      for (int c0 = 0; c0 < p.sk_pad; c0 += 16) {
+      const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? row : 0);
+      // pass 2: P = exp2(s * scale * log2e - max), bf16, into the swizzled A-operand tile
+      for (c0 = 0; c0 < p.sk_pad; c0 += 16) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_S + lane_addr + c0, r);
         tmem_ld_wait();
         uint32_t packed[8];
+        if (c0 + 16 <= p.Sk && !p.dropout_thr16) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float e0 = 0.0f, e1 = 0.0f;
-          if (c0 + i < p.Sk) { e0 = exp2f(__uint_as_float(r[i]) * sl2 - mxs); sum += e0; e0 *= drop_mul(p, bh, drow, c0 + i); }
-          if (c0 + i + 1 < p.Sk) { e1 = exp2f(__uint_as_float(r[i + 1]) * sl2 - mxs); sum += e1; e1 *= drop_mul(p, bh, drow, c0 + i + 1); }
-          packed[i >> 1] = pack_bf16x2(e0, e1);
+          for (int i = 0; i < 16; i += 2) {
+            const float e0 = exp2f(__uint_as_float(r[i]) * sl2 - mxs), e1 = exp2f(__uint_as_float(r[i + 1]) * sl2 - mxs);
+            sum += e0 + e1;
+            packed[i >> 1] = pack_bf16x2(e0, e1);
+          }
+        } else {
+          float m[16];
+          if (p.dropout_thr16) {
+            drop_mul16(p, rowkey, c0, m);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m[i] = 1.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float e0 = 0.0f, e1 = 0.0f;
+            if (c0 + i < p.Sk) { e0 = exp2f(__uint_as_float(r[i]) * sl2 - mxs); sum += e0; e0 *= m[i]; }
+            if (c0 + i + 1 < p.Sk) { e1 = exp2f(__uint_as_float(r[i + 1]) * sl2 - mxs); sum += e1; e1 *= m[i + 1]; }
+            packed[i >> 1] = pack_bf16x2(e0, e1);
+          }
         }
-        // 16 columns = two 16-byte chunks of row `tid` in k-block c0/64
-        uint8_t* blk = sP + (c0 >> 6) * 16384;
+        const uint32_t blk = smem_u32(sP + (c0 >> 6) * 16384);
         const int ch = (c0 & 63) >> 3;
-        *reinterpret_cast<uint4*>(blk + sw128(tid, ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        *reinterpret_cast<uint4*>(blk + sw128(tid, ch + 1)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        sts128(blk + sw128(tid, ch), packed[0], packed[1], packed[2], packed[3]);
+        sts128(blk + sw128(tid, ch + 1), packed[4], packed[5], packed[6], packed[7]);
       }
       fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
     }
@@ -182,16 +293,18 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const __grid_constant__ C
       const float inv = 1.0f / sum;
       __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + (row_ok ? row : 0)) * p.ldo + h * HD;
 #pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(tmem_O + lane_addr + c0, r);
+      for (int c0 = 0; c0 < HD; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_addr + c0, r);
         tmem_ld_wait();
         if (row_ok) {
-          uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) pk[i >> 1] = pack_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk[i] = pack_bf16x2(__uint_as_float(r[8 * g + 2 * i]) * inv, __uint_as_float(r[8 * g + 2 * i + 1]) * inv);
+            *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
         }
       }
       if (row_ok && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + row] = mx * p.scale + __logf(sum);
@@ -200,6 +313,7 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const __grid_constant__ C
     __syncthreads();   // TMEM S/O, sQ and sP are reused by the next m-tile
     tc_fence_after();
   }
+  if (m_tiles == 0) __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -436,6 +550,342 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const __grid_constant__ C
   if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------- backward, v2
+// Sq <= 128 + kMaxTail: ONE 128-row tensor-core tile + tail query rows on CUDA cores (warp 5); keys in chunks
+// of <= 144 (the 129-token sequences are one chunk).  Per chunk:
+//   issuer   S = Q K^T, dP = dO V^T                         (N = nk <= 144)
+//   workers  P, dS -> bf16 swizzled smem tiles (3 k-blocks)  | tail warp: p, ds of the tail rows (smem vectors)
+//   issuer   dV = P^T dO, dK = dS^T Q (keys 0..127 of the chunk), dQ += dS K
+//   workers  drain dK / dV rows, add the tail rows' rank-1 terms, store
+//   if nk > 128: issuer recomputes dV / dK for keys 128..nk-1 from the third k-block (same TMEM columns)
+// TMEM: S [0,144) | dP [160,304) | dK [320,384) | dV [384,448) | dQ [448,512)
+// smem: Q 16K | dO 16K | P 48K | dS 48K | K 18K | V 18K | barriers | D, lse | tail scratch
+constexpr int kThreadsBwd2 = 192;
+constexpr int KC = 144;
+
+__global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                                                            const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + 16384;
+  uint8_t* sP = sdO + 16384;        // 3 k-blocks
+  uint8_t* sdS = sP + 3 * 16384;    // 3 k-blocks; block 2 + 16 KB falls into sK (valid, finite data)
+  uint8_t* sK = sdS + 3 * 16384;
+  uint8_t* sV = sK + KC * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KC * 128);
+  uint64_t* bar_q = bars;           // Q and dO tiles landed
+  uint64_t* bar_kv = bars + 1;      // K / V chunk landed          (one phase per chunk)
+  uint64_t* bar_s = bars + 2;       // S and dP complete           (one phase per chunk)
+  uint64_t* bar_g = bars + 3;       // dV, dK, dQ MMAs complete    (one phase per chunk)
+  uint64_t* bar_t = bars + 4;       // tail-key dV, dK complete    (one phase per chunk that has tail keys)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* sD = reinterpret_cast<float*>(bars + 8);   // [128]
+  float* sL = sD + 128;                             // [128] lse * log2e
+  float* tq = sL + 128;                             // [kMaxTail][64] tail query rows
+  float* tdo = tq + kMaxTail * HD;                  // [kMaxTail][64] tail dO rows
+  float* tdq = tdo + kMaxTail * HD;                 // [kMaxTail][64] tail dQ accumulators
+  float* tp = tdq + kMaxTail * HD;                  // [kMaxTail][KC] P * mask of the tail rows, this chunk
+  float* tds = tp + kMaxTail * KC;                  // [kMaxTail][KC] dS of the tail rows, this chunk
+  float* tDL = tds + kMaxTail * KC;                 // [kMaxTail][2]  D_t, lse_t * log2e
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = warp == 4 && lane == 0;
+  const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
+  const int n_main = p.Sq < 128 ? p.Sq : 128;       // valid rows of the tensor-core tile
+  const int ntail = p.Sq - n_main;                  // rows handled by warp 5
+  if (issuer) {
+    mbar_init(smem_u32(bar_q), 1);
+    mbar_init(smem_u32(bar_kv), 1);
+    mbar_init(smem_u32(bar_s), 1);
+    mbar_init(smem_u32(bar_g), 1);
+    mbar_init(smem_u32(bar_t), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 160, tdK = tmem_base + 320, tdV = tmem_base + 384, tdQ = tmem_base + 448;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const float sl2 = p.scale * kLog2e;
+
+  if (issuer) {
+    mbar_arrive_expect_tx(smem_u32(bar_q), 2 * 16384);
+    tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq);
+    tma_load_2d(smem_u32(sdO), &tmdO, smem_u32(bar_q), h * HD, b * p.Sq);
+  }
+  if (warp < 4) {
+    // D_i = sum_c dO_ic O_ic and lse_i for the main rows, straight from global memory
+    float acc = 0.0f, l = 0.0f;
+    if (tid < n_main) {
+      const __nv_bfloat16* orow = p.o_in + (static_cast<long long>(b) * p.Sq + tid) * p.ldo + h * HD;
+      const __nv_bfloat16* drow = p.do_in + (static_cast<long long>(b) * p.Sq + tid) * p.lddo + h * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 8) {
+        float a[8], d[8];
+        Vec16<__nv_bfloat16>::load(orow + c, a);
+        Vec16<__nv_bfloat16>::load(drow + c, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += a[i] * d[i];
+      }
+      l = p.lse[static_cast<long long>(bh) * p.Sq + tid] * kLog2e;
+    }
+    sD[tid] = acc;
+    sL[tid] = l;
+  } else if (warp == 5) {
+    for (int t = 0; t < ntail; ++t) {
+      const long long grow = static_cast<long long>(b) * p.Sq + n_main + t;
+      const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.q_in + grow * p.ldq + h * HD + 2 * lane));
+      const float2 d2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.do_in + grow * p.lddo + h * HD + 2 * lane));
+      const float2 o2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.o_in + grow * p.ldo + h * HD + 2 * lane));
+      tq[t * HD + 2 * lane] = q2.x; tq[t * HD + 2 * lane + 1] = q2.y;
+      tdo[t * HD + 2 * lane] = d2.x; tdo[t * HD + 2 * lane + 1] = d2.y;
+      tdq[t * HD + 2 * lane] = 0.0f; tdq[t * HD + 2 * lane + 1] = 0.0f;
+      const float Dt = warp_sum(d2.x * o2.x + d2.y * o2.y);
+      if (lane == 0) {
+        tDL[2 * t] = Dt;
+        tDL[2 * t + 1] = p.lse[static_cast<long long>(bh) * p.Sq + n_main + t] * kLog2e;
+      }
+    }
+  }
+  __syncthreads();
+
+  uint32_t phase = 0, t_phase = 0;
+  for (int k0 = 0; k0 < p.Sk; k0 += KC, phase ^= 1) {
+    const int nk = p.sk_pad - k0 < KC ? p.sk_pad - k0 : KC;   // padded keys in this chunk (multiple of 16)
+    if (issuer) {
+      mbar_arrive_expect_tx(smem_u32(bar_kv), 2 * nk * 128);
+      for (int r = 0; r < nk; r += 16) {
+        tma_load_2d(smem_u32(sK + r * 128), &tmK, smem_u32(bar_kv), h * HD, b * p.Sk + k0 + r);
+        tma_load_2d(smem_u32(sV + r * 128), &tmV, smem_u32(bar_kv), h * HD, b * p.Sk + k0 + r);
+      }
+      if (k0 == 0) mbar_wait(smem_u32(bar_q), 0);
+      mbar_wait(smem_u32(bar_kv), phase);
+      tc_fence_after();
+      mma_kk(tS, smem_u32(sQ), smem_u32(sK), nk);      // S  = Q K^T
+      mma_kk(tdP, smem_u32(sdO), smem_u32(sV), nk);    // dP = dO V^T
+      tc_commit(smem_u32(bar_s));
+    }
+    if (warp < 4) {
+      mbar_wait(smem_u32(bar_s), phase);
+      tc_fence_after();
+      const bool row_ok = tid < n_main;
+      if (warp * 32 < n_main) {
+        const float Di = sD[tid], Li = sL[tid];
+        const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? tid : 0);
+        for (int c0 = 0; c0 < nk; c0 += 16) {
+          uint32_t rs[16], rp[16];
+          tmem_ld_32x32b_x16(tS + lane_addr + c0, rs);
+          tmem_ld_32x32b_x16(tdP + lane_addr + c0, rp);
+          tmem_ld_wait();
+          float m[16];
+          if (p.dropout_thr16) {
+            drop_mul16(p, rowkey, k0 + c0, m);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m[i] = 1.0f;
+          }
+          uint32_t pp[8], pd[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float pr[2], ds[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              float prob = 0.0f, dsv = 0.0f;
+              if (row_ok && k0 + c0 + i + u < p.Sk) {
+                prob = exp2f(__uint_as_float(rs[i + u]) * sl2 - Li);
+                dsv = prob * (__uint_as_float(rp[i + u]) * m[i + u] - Di) * p.scale;
+                prob *= m[i + u];
+              }
+              pr[u] = prob;
+              ds[u] = dsv;
+            }
+            pp[i >> 1] = pack_bf16x2(pr[0], pr[1]);
+            pd[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+          }
+          const uint32_t blk = (c0 >> 6) * 16384;
+          const int ch = (c0 & 63) >> 3;
+          sts128(smem_u32(sP) + blk + sw128(tid, ch), pp[0], pp[1], pp[2], pp[3]);
+          sts128(smem_u32(sP) + blk + sw128(tid, ch + 1), pp[4], pp[5], pp[6], pp[7]);
+          sts128(smem_u32(sdS) + blk + sw128(tid, ch), pd[0], pd[1], pd[2], pd[3]);
+          sts128(smem_u32(sdS) + blk + sw128(tid, ch + 1), pd[4], pd[5], pd[6], pd[7]);
+        }
+      } else {
+        // query rows beyond the sequence feed the contraction of dV / dK: they must be zero
+        for (int c0 = 0; c0 < nk; c0 += 8) {
+          const uint32_t off = (c0 >> 6) * 16384 + sw128(tid, (c0 & 63) >> 3);
+          sts128(smem_u32(sP) + off, 0, 0, 0, 0);
+          sts128(smem_u32(sdS) + off, 0, 0, 0, 0);
+        }
+      }
+      fence_proxy_async_smem();
+    } else if (warp == 5 && ntail > 0) {
+      // tail query rows against this key chunk (CUDA cores), K / V read from the swizzled smem tiles
+      mbar_wait(smem_u32(bar_kv), phase);
+      for (int t = 0; t < ntail; ++t) {
+        const float Dt = tDL[2 * t], Lt = tDL[2 * t + 1];
+        const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, n_main + t);
+        for (int j = lane; j < nk; j += 32) {
+          float pm = 0.0f, dsv = 0.0f;
+          if (k0 + j < p.Sk) {
+            float sacc = 0.0f, dacc = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float kf[8], vf[8];
+              Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(j, c)), kf);
+              Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(j, c)), vf);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                sacc += tq[t * HD + c * 8 + i] * kf[i];
+                dacc += tdo[t * HD + c * 8 + i] * vf[i];
+              }
+            }
+            float m = 1.0f;
+            if (p.dropout_thr16) {
+              const uint64_t bits = attn_drop_bits(p.dropout_seed, rowkey, (k0 + j) >> 2);
+              m = dropout_keep_lane(bits, (k0 + j) & 3, p.dropout_thr16) ? p.dropout_scale : 0.0f;
+            }
+            const float prob = exp2f(sacc * sl2 - Lt);
+            dsv = prob * (dacc * m - Dt) * p.scale;
+            pm = prob * m;
+          }
+          tp[t * KC + j] = pm;
+          tds[t * KC + j] = dsv;
+        }
+        __syncwarp();
+        float a0 = tdq[t * HD + 2 * lane], a1 = tdq[t * HD + 2 * lane + 1];
+        for (int j = 0; j < nk; ++j) {
+          const float dsj = tds[t * KC + j];
+          const float2 k2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sw_elem(sK, j, 2 * lane)));
+          a0 += dsj * k2.x;
+          a1 += dsj * k2.y;
+        }
+        tdq[t * HD + 2 * lane] = a0;
+        tdq[t * HD + 2 * lane + 1] = a1;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (issuer) {
+      tc_fence_after();
+      // dV = P^T dO, dK = dS^T Q for keys 0..127 of the chunk: A MN-major (two 64-key blocks, LBO 16 KB), contraction over queries
+      const uint32_t idesc_mn = make_idesc_bf16(128, HD, true, true);
+      for (int k = 0; k < 8; ++k) {
+        const uint64_t bd = make_smem_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024);
+        const uint64_t bq = make_smem_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024);
+        tc_mma_f16_ss(tdV, make_smem_desc_sw128(smem_u32(sP) + k * 2048, 16384, 1024), bd, idesc_mn, k > 0);
+        tc_mma_f16_ss(tdK, make_smem_desc_sw128(smem_u32(sdS) + k * 2048, 16384, 1024), bq, idesc_mn, k > 0);
+      }
+      // dQ += dS K: contraction over the nk keys of this chunk
+      const uint32_t idesc_q = make_idesc_bf16(128, HD, false, true);
+      for (int k = 0; k < nk / 16; ++k) {
+        const uint32_t a = smem_u32(sdS + (k >> 2) * 16384) + (k & 3) * 32;
+        tc_mma_f16_ss(tdQ, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_q,
+                      (k0 > 0 || k > 0));
+      }
+      tc_commit(smem_u32(bar_g));
+    }
+    // drain dK / dV (thread == key row of the chunk), add the tail query rows' rank-1 terms
+    auto drain_keys = [&](int jbase) {
+      const int j = jbase + tid;                 // key index inside the chunk
+      const int key = k0 + j;
+      const bool ok = key < p.Sk;
+      __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * p.lddk + h * HD;
+      __nv_bfloat16* dvrow = p.dv + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * p.lddv + h * HD;
+#pragma unroll
+      for (int c0 = 0; c0 < HD; c0 += 16) {
+        uint32_t rk[16], rv[16];
+        tmem_ld_32x32b_x16(tdK + lane_addr + c0, rk);
+        tmem_ld_32x32b_x16(tdV + lane_addr + c0, rv);
+        tmem_ld_wait();
+        if (ok) {
+          float fk[16], fv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { fk[i] = __uint_as_float(rk[i]); fv[i] = __uint_as_float(rv[i]); }
+          for (int t = 0; t < ntail; ++t) {
+            const float dsj = tds[t * KC + j], pj = tp[t * KC + j];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              fk[i] += dsj * tq[t * HD + c0 + i];
+              fv[i] += pj * tdo[t * HD + c0 + i];
+            }
+          }
+          uint32_t a[8], c[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            a[i >> 1] = pack_bf16x2(fk[i], fk[i + 1]);
+            c[i >> 1] = pack_bf16x2(fv[i], fv[i + 1]);
+          }
+          *reinterpret_cast<uint4*>(dkrow + c0) = make_uint4(a[0], a[1], a[2], a[3]);
+          *reinterpret_cast<uint4*>(dkrow + c0 + 8) = make_uint4(a[4], a[5], a[6], a[7]);
+          *reinterpret_cast<uint4*>(dvrow + c0) = make_uint4(c[0], c[1], c[2], c[3]);
+          *reinterpret_cast<uint4*>(dvrow + c0 + 8) = make_uint4(c[4], c[5], c[6], c[7]);
+        }
+      }
+    };
+    if (warp < 4) {
+      mbar_wait(smem_u32(bar_g), phase);
+      tc_fence_after();
+      if (k0 + warp * 32 < p.Sk) drain_keys(0);
+    }
+    if (nk > 128) {
+      tc_fence_before();
+      __syncthreads();          // dK / dV accumulators drained: reuse them for keys 128.. of the chunk
+      if (issuer) {
+        tc_fence_after();
+        const uint32_t idesc_mn = make_idesc_bf16(128, HD, true, true);
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t bd = make_smem_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024);
+          const uint64_t bq = make_smem_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024);
+          tc_mma_f16_ss(tdV, make_smem_desc_sw128(smem_u32(sP) + 2 * 16384 + k * 2048, 16384, 1024), bd, idesc_mn, k > 0);
+          tc_mma_f16_ss(tdK, make_smem_desc_sw128(smem_u32(sdS) + 2 * 16384 + k * 2048, 16384, 1024), bq, idesc_mn, k > 0);
+        }
+        tc_commit(smem_u32(bar_t));
+      }
+      if (warp < 4) {
+        mbar_wait(smem_u32(bar_t), t_phase);
+        tc_fence_after();
+        if (warp * 32 < nk - 128 && k0 + 128 + warp * 32 < p.Sk) drain_keys(128);
+      }
+      t_phase ^= 1;
+    }
+    tc_fence_before();
+    __syncthreads();   // K / V / P / dS buffers and the dK / dV accumulators are reused by the next chunk
+    tc_fence_after();
+  }
+  // dQ: main rows from TMEM, tail rows from the CUDA-core accumulators
+  if (warp < 4 && warp * 32 < n_main) {
+    __nv_bfloat16* dqrow = p.dq + (static_cast<long long>(b) * p.Sq + (tid < n_main ? tid : 0)) * p.lddq + h * HD;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tdQ + lane_addr + c0, r);
+      tmem_ld_wait();
+      if (tid < n_main) {
+        uint32_t a[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) a[i >> 1] = pack_bf16x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        *reinterpret_cast<uint4*>(dqrow + c0) = make_uint4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<uint4*>(dqrow + c0 + 8) = make_uint4(a[4], a[5], a[6], a[7]);
+      }
+    }
+  } else if (warp == 5) {
+    for (int t = 0; t < ntail; ++t) {
+      __nv_bfloat16* dqrow = p.dq + (static_cast<long long>(b) * p.Sq + n_main + t) * p.lddq + h * HD;
+      *reinterpret_cast<__nv_bfloat162*>(dqrow + 2 * lane) = __floats2bfloat162_rn(tdq[t * HD + 2 * lane], tdq[t * HD + 2 * lane + 1]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -453,7 +903,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // [rows, width] bf16 matrix with row pitch ld, boxes of 16 rows x 64 columns, 128B swizzle.
-static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long width, long long ld) {
+static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long width, long long ld, int box_rows = 16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -461,7 +911,7 @@ static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long w
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64, 16};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -496,13 +946,16 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
   CUtensorMap tq, tk, tv;
   const long long w = a->heads * HD;
   int rc;
-  if ((rc = make_map(&tq, a->q, a->batch * a->sq, w, a->ldq)) != TVT_OK) return rc;
-  if ((rc = make_map(&tk, a->k, a->batch * a->sk, w, a->ldk)) != TVT_OK) return rc;
-  if ((rc = make_map(&tv, a->v, a->batch * a->sk, w, a->ldv)) != TVT_OK) return rc;
+  p.kv_box = p.sk_pad % 48 == 0 ? 48 : (p.sk_pad % 32 == 0 ? 32 : 16);
+  if (p.sk_pad % 128 == 0) p.kv_box = 128;
+  p.q_in = (const __nv_bfloat16*)a->q; p.ldq = a->ldq;
+  if ((rc = make_map(&tq, a->q, a->batch * a->sq, w, a->ldq, 128)) != TVT_OK) return rc;
+  if ((rc = make_map(&tk, a->k, a->batch * a->sk, w, a->ldk, p.kv_box)) != TVT_OK) return rc;
+  if ((rc = make_map(&tv, a->v, a->batch * a->sk, w, a->ldv, p.kv_box)) != TVT_OK) return rc;
   const int kv = ((p.sk_pad * 128) + 1023) & ~1023;
-  const size_t bytes = 1024 + 16384 + 2 * (size_t)kv + (size_t)((p.sk_pad + 63) / 64) * 16384 + 64;
+  const size_t bytes = 1024 + 16384 + 2 * (size_t)kv + (size_t)((p.sk_pad + 63) / 64) * 16384 + 64 + (HD + p.sk_pad) * 4;
   if ((rc = set_smem(fwd_kernel, bytes, "tvt_attention_fwd")) != TVT_OK) return rc;
-  fwd_kernel<<<p.B * p.H, kThreads, bytes, s>>>(tq, tk, tv, p);
+  fwd_kernel<<<p.B * p.H, kThreadsFwd, bytes, s>>>(tq, tk, tv, p);
   return check_launch("tvt_attention_fwd");
 }
 
@@ -525,6 +978,16 @@ int launch_bwd(const tvt_attention_bwd_args* a, cudaStream_t s) {
   if ((rc = make_map(&tk, a->k, a->batch * a->sk, w, a->ldk)) != TVT_OK) return rc;
   if ((rc = make_map(&tv, a->v, a->batch * a->sk, w, a->ldv)) != TVT_OK) return rc;
   if ((rc = make_map(&tdo, a->d_o, a->batch * a->sq, w, a->lddo)) != TVT_OK) return rc;
+  if (p.Sq <= 128 + kMaxTail) {
+    CUtensorMap tq128, tdo128;
+    if ((rc = make_map(&tq128, a->q, a->batch * a->sq, w, a->ldq, 128)) != TVT_OK) return rc;
+    if ((rc = make_map(&tdo128, a->d_o, a->batch * a->sq, w, a->lddo, 128)) != TVT_OK) return rc;
+    p.q_in = (const __nv_bfloat16*)a->q; p.ldq = a->ldq;
+    const size_t bytes2 = 1024 + 2 * 16384 + 6 * 16384 + 2 * (size_t)KC * 128 + 64 + 256 * 4 + (3 * kMaxTail * HD + 2 * kMaxTail * KC + 2 * kMaxTail) * 4;
+    if ((rc = set_smem(bwd2_kernel, bytes2, "tvt_attention_bwd")) != TVT_OK) return rc;
+    bwd2_kernel<<<p.B * p.H, kThreadsBwd2, bytes2, s>>>(tq128, tk, tv, tdo128, p);
+    return check_launch("tvt_attention_bwd");
+  }
   const int m_tiles = (p.Sq + 127) / 128;
   const size_t bytes = 1024 + (size_t)m_tiles * 32768 + 2 * 16384 + 2 * 32768 + 64 + (size_t)m_tiles * 128 * 8;
   if ((rc = set_smem(bwd_kernel, bytes, "tvt_attention_bwd")) != TVT_OK) return rc;

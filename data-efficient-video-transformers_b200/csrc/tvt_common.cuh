@@ -140,6 +140,17 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t elem, uint3
   return dropout_keep_lane(dropout_bits4(seed, elem >> 2), static_cast<int>(elem & 3), thr16);
 }
 
+// Attention-probability dropout: the mask of (clip*head bh, query row i, key j) is lane (j & 3) of the
+// 64 bits hashed from ((bh * Sq + i) * ceil(Sk / 4) + j / 4), so a thread that owns a query row needs one
+// hash per 4 consecutive keys.  Shared by the CUDA-core and the tcgen05 kernels (forward of one may be
+// paired with the backward of the other).
+__device__ __forceinline__ uint64_t attn_drop_bits(uint64_t seed, uint64_t rowkey, int j4) {
+  return dropout_bits4(seed, rowkey + static_cast<uint64_t>(j4));
+}
+__device__ __forceinline__ uint64_t attn_rowkey(long long bh, int sq, int sk, int i) {
+  return (static_cast<uint64_t>(bh) * sq + i) * static_cast<uint64_t>((sk + 3) >> 2);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace tvt
