@@ -345,6 +345,11 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    traffic = None
+    try:   # dram__bytes_read + write per launch from the committed ncu --set full capture of this kernel
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))["mean_dram_bytes_per_launch"]
+    except Exception:
+        pass
     total_ms = sum(v["ms"] for v in breakdown.values()) or 1.0
     fl = flops_per_clip(w)
     value = world * B / (ms * 1e-3)
@@ -363,7 +368,7 @@ def main():
         "model_tflops": round(value / world * fl / 1e12, 1),
         "model_frac_of_peak": round(value / world * fl / 1e12 / peak_tf, 4),
         "roofline": {"kernel": "tvt::gemm::gemm_kernel (tcgen05)", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                     "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": traffic, "peak_source": peak_src,
                      "launches_per_step": gemm["calls"], "share_of_kernel_time": round(gemm["ms"] / total_ms, 4)},
     }
     if not args.no_cpu_baseline:

@@ -195,21 +195,25 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
   // the plain bf16 output (the hot path) is staged through shared memory by the caller
 }
 
-// Warp-cooperative fetch of a [32 rows x 32 bf16] block of a row-major matrix: global reads are coalesced
-// (4 lanes x 16 B per row, 8 rows per pass), the block is transposed to "one row per lane" through the
-// warp's swizzled staging buffer.  Rows >= M / columns >= N read as zero.
-__device__ __forceinline__ void fetch_rows32(const void* base, long long ld, long long row0, int col0, int M, int N,
-                                             uint32_t stage_addr, int lane, uint32_t (&out)[16]) {
+// Warp-cooperative fetch of a [32 rows x 32 bf16] block of a row-major matrix, in two halves so the global
+// loads of the NEXT chunk can be in flight while the current chunk is processed:
+//   fetch_issue: coalesced global reads (4 lanes x 16 B per row, 8 rows per pass) into registers;
+//   fetch_land:  transpose to "one row per lane" through the warp's swizzled staging buffer.
+// Rows >= M / columns >= N read as zero.
+__device__ __forceinline__ void fetch_issue(const void* base, long long ld, long long row0, int col0, int M, int N, int lane,
+                                            uint4 (&t)[4]) {
   const int seg = lane & 3;
   const int gcol = col0 + seg * 8;
   const __nv_bfloat16* gptr = reinterpret_cast<const __nv_bfloat16*>(base) + (row0 + (lane >> 2)) * ld + gcol;
-  uint4 t[4];
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int rr = ps * 8 + (lane >> 2);
     t[ps] = make_uint4(0, 0, 0, 0);
     if (row0 + rr < M && gcol < N) t[ps] = __ldg(reinterpret_cast<const uint4*>(gptr + static_cast<long long>(ps) * 8 * ld));
   }
+}
+__device__ __forceinline__ void fetch_land(const uint4 (&t)[4], uint32_t stage_addr, int lane, uint32_t (&out)[16]) {
+  const int seg = lane & 3;
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int rr = ps * 8 + (lane >> 2);
@@ -370,21 +374,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int split = (w / num_n) / num_m;
       const int kb0 = static_cast<int>(static_cast<long long>(split) * kb_total / p.splits);
       const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
-      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
-      tc_fence_after();
       const long long row0 = static_cast<long long>(m_blk) * BM + quad * 32;
       const long long row = row0 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
+      // operands of the fused stages that live in global memory are fetched coalesced (one warp = 32 rows) and
+      // one chunk ahead: the first fetch is issued before waiting for the accumulator, the next one while the
+      // current chunk is processed
+      const bool pre = !p.atomic_out;
+      const bool pre_res = pre && p.residual && !p.residual_f32;
+      const bool pre_mask = pre && p.relu_mask && !p.mask_f32;
+      const int colbase = n_blk * BN + half * (BN / 2);
+      uint4 pf[4];
+      if (pre_res) fetch_issue(p.residual, p.ld_residual, row0, colbase, p.M, p.N, lane, pf);
+      else if (pre_mask) fetch_issue(p.relu_mask, p.ld_mask, row0, colbase, p.M, p.N, lane, pf);
+      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         const int tcol = half * (BN / 2) + c * 32;   // column inside the tile
         const int col0 = n_blk * BN + tcol;
         if (col0 >= p.N) break;  // warp-uniform
-        // operands of the fused stages that live in global memory: fetched coalesced, one warp = 32 rows
         uint32_t mask_pk[16], res_pk[16];
-        const bool pre = !p.atomic_out;
-        if (pre && p.relu_mask && !p.mask_f32) fetch_rows32(p.relu_mask, p.ld_mask, row0, col0, p.M, p.N, stage_addr, lane, mask_pk);
-        if (pre && p.residual && !p.residual_f32) fetch_rows32(p.residual, p.ld_residual, row0, col0, p.M, p.N, stage_addr, lane, res_pk);
+        if (pre_res) {
+          fetch_land(pf, stage_addr, lane, res_pk);
+          if (c + 1 < BN / 64) fetch_issue(p.residual, p.ld_residual, row0, col0 + 32, p.M, p.N, lane, pf);
+          if (pre_mask) {   // both (not on the hot path): the mask is fetched in place
+            uint4 t[4];
+            fetch_issue(p.relu_mask, p.ld_mask, row0, col0, p.M, p.N, lane, t);
+            fetch_land(t, stage_addr, lane, mask_pk);
+          }
+        } else if (pre_mask) {
+          fetch_land(pf, stage_addr, lane, mask_pk);
+          if (c + 1 < BN / 64) fetch_issue(p.relu_mask, p.ld_mask, row0, col0 + 32, p.M, p.N, lane, pf);
+        }
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + tcol, r);
         tmem_ld_wait();

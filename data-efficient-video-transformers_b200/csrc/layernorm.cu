@@ -287,16 +287,20 @@ static int dispatch_chunks(const P& p, int d, cudaStream_t s) {
   return TVT_EINVAL;
 }
 
-static int grid_for(long long rows) {
-  const long long want = (rows + kWarps - 1) / kWarps;
-  const long long cap = static_cast<long long>(num_sms()) * 8;
+// One persistent wave: grid = SMs x resident CTAs per SM (queried per kernel), capped by the row count.
+template <typename K>
+static int grid_for(K kern, int threads, long long rows, int warps_per_cta) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0) != cudaSuccess || occ < 1) occ = 2;
+  const long long want = (rows + warps_per_cta - 1) / warps_per_cta;
+  const long long cap = static_cast<long long>(num_sms()) * occ;
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
 template <typename T, int C>
 struct FwdLauncher {
   static int run(const FwdParams& p, cudaStream_t s) {
-    ln_fwd_kernel<T, C><<<grid_for(p.rows), kWarps * 32, 0, s>>>(p);
+    ln_fwd_kernel<T, C><<<grid_for(ln_fwd_kernel<T, C>, kWarps * 32, p.rows, kWarps), kWarps * 32, 0, s>>>(p);
     return check_launch("tvt_layernorm_fwd");
   }
 };
@@ -304,9 +308,7 @@ template <typename T, int C>
 struct BwdLauncher {
   static int run(const BwdParams& p, cudaStream_t s) {
     // fewer, fatter CTAs: each ends with d atomics per output vector
-    const long long want = (p.rows + kBwdWarps * 4 - 1) / (kBwdWarps * 4);
-    const long long cap = static_cast<long long>(num_sms()) * 3;
-    const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+    const int grid = grid_for(ln_bwd_kernel<T, C>, kBwdWarps * 32, (p.rows + 3) / 4, kBwdWarps);
     ln_bwd_kernel<T, C><<<grid, kBwdWarps * 32, 0, s>>>(p);
     return check_launch("tvt_layernorm_bwd");
   }

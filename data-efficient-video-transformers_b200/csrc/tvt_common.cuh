@@ -120,17 +120,22 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 // Counter-based dropout mask: keep(element) is a pure function of (seed, element index), so the
-// backward pass regenerates the forward mask instead of storing it. One 64-bit mix (splitmix64
-// finaliser) yields 4 independent 16-bit lanes; callers pass idx = element_index / 4.
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-// 64 random bits covering the 4 consecutive elements [4*elem_div4, 4*elem_div4 + 4).
+// backward pass regenerates the forward mask instead of storing it.  One Philox-2x32 evaluation (5 rounds:
+// the fewest whose keep-bits show no measurable lag / cross-seed correlation on 2^21-element streams, see
+// DESIGN.md) yields 64 bits = 4 independent 16-bit lanes for 4 consecutive elements; ~15 integer
+// instructions per 4 elements.
 __device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t elem_div4) {
-  return mix64(seed ^ (elem_div4 * 0xD6E8FEB86659FD93ull));
+  uint32_t R = static_cast<uint32_t>(elem_div4);
+  uint32_t L = static_cast<uint32_t>(elem_div4 >> 32) ^ static_cast<uint32_t>(seed >> 32);
+  uint32_t k = static_cast<uint32_t>(seed);
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const uint64_t m = static_cast<uint64_t>(R) * 0xD256D193ull;
+    R = static_cast<uint32_t>(m >> 32) ^ k ^ L;
+    L = static_cast<uint32_t>(m);
+    k += 0x9E3779B9u;
+  }
+  return (static_cast<uint64_t>(L) << 32) | R;
 }
 // Lane i (0..3) survives dropout when its 16 random bits are >= thr16 (= p * 65536).
 __device__ __forceinline__ bool dropout_keep_lane(uint64_t bits, int i, uint32_t thr16) {
