@@ -41,7 +41,7 @@ class LayerNormFwdArgs(C.Structure):
 class LayerNormBwdArgs(C.Structure):
     _fields_ = [("dy", vp), ("x", vp), ("mean", vp), ("rstd", vp), ("gamma", vp), ("dx", vp), ("dz", vp),
                 ("dfeat", vp), ("dcls", vp), ("dgamma", vp), ("dbeta", vp), ("dbias", vp), ("rows", i64),
-                ("d", i64), ("seq_len", i64), ("dtype", i32), ("dropout_p", f32), ("dropout_seed", u64)]
+                ("d", i64), ("seq_len", i64), ("dtype", i32), ("dropout_p", f32), ("dropout_seed", u64), ("dres", vp)]
 
 
 class AttentionFwdArgs(C.Structure):

@@ -143,6 +143,7 @@ struct BwdParams {
   long long rows; int d; int S;
   float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
   long long dropout_ld;  // row pitch used for dropout element indices (N of the producing GEMM)
+  const void* dres;      // optional residual-path gradient added to dx
 };
 
 constexpr int kBwdWarps = 4;
@@ -234,6 +235,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32) ln_bwd_kernel(const BwdParams 
         float o[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+        if (p.dres) {
+          float rr[V];
+          Vec16<T>::load(reinterpret_cast<const T*>(p.dres) + row * p.d + col, rr);
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] += rr[i];
+        }
         if (dx_row) Vec16<T>::store(dx_row + col, o);
         if (p.dropout_thr16) {
 #pragma unroll
@@ -379,6 +386,9 @@ extern "C" int tvt_layernorm_bwd(const tvt_layernorm_bwd_args* a, void* stream) 
     p.dropout_seed = a->dropout_seed;
   }
   p.dropout_ld = a->d;
+  p.dres = a->dres;
+  TVT_REQUIRE(!(a->dres && (a->dz || a->seq_len > 0 || a->dropout_p > 0.0f)), "tvt_layernorm_bwd: dres cannot be combined with dz / embed mode / dropout");
+  TVT_REQUIRE(al16(a->dres), "tvt_layernorm_bwd: dres must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::BwdLauncher>(p, p.d, s)
                              : ln::dispatch_chunks<__nv_bfloat16, ln::BwdLauncher>(p, p.d, s);

@@ -142,6 +142,82 @@ class EncoderLayerFn(torch.autograd.Function):
         return (None, dx, dmem, dinw, dinb, dow, dob, dl1w, dl1b, dl2w, dl2b, dn1w, dn1b, dn2w, dn2b)
 
 
+class PreNormLayerFn(torch.autograd.Function):
+    """Pre-norm block of src/models/vit.py:8-75:  x1 = x + Drop(OutProj(Attn(LN1(x))));  out = x1 + Drop(W2 Drop(gelu(W1 LN2(x1)))).
+    Bias-free packed qkv projection [3*inner, dim] (vit.py:39), scale = dim_head ** -0.5 (vit.py:37),
+    inner = heads * dim_head may differ from dim; out_w is None when the reference uses nn.Identity (vit.py:41-44)."""
+
+    @staticmethod
+    def forward(ctx, cfg, dim_head, x, n1_w, n1_b, qkv_w, out_w, out_b, n2_w, n2_b, l1_w, l1_b, l2_w, l2_b):
+        m = cfg.mode
+        n, d = x.shape
+        B, H = cfg.B, cfg.H
+        S, inner, ff = n // B, H * dim_head, l1_w.shape[0]
+        p = cfg.p
+        seeds = [next_seed() for _ in range(3)] if p > 0 else [0, 0, 0]
+        xn, mean1, rstd1 = ops.layernorm_fwd(x, n1_w, n1_b)
+        qkv = m.linear_fwd(m.split(xn), n, d, qkv_w, None)
+        scale = dim_head ** -0.5
+        attn, lse = ops.attention_fwd(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], B, H, S, S, dim_head, scale,
+                                      impl=cfg.attn_impl)
+        if out_w is not None:
+            x1 = m.linear_fwd(m.split(attn), n, inner, out_w, out_b, residual=x, dropout_p=p, seed=seeds[0])
+        else:   # heads == 1 and dim_head == dim: no output projection, no dropout (vit.py:41-44)
+            x1 = attn + x
+        xn2, mean2, rstd2 = ops.layernorm_fwd(x1, n2_w, n2_b)
+        z = m.empty(n, ff, device=x.device)
+        h = m.linear_fwd(m.split(xn2), n, d, l1_w, l1_b, act=ACT_GELU, dropout_p=p, seed=seeds[1], preact=z)
+        out = m.linear_fwd(m.split(h), n, ff, l2_w, l2_b, residual=x1, dropout_p=p, seed=seeds[2])
+        ctx.cfg, ctx.seeds, ctx.dims = cfg, seeds, (n, d, B, H, dim_head, S, inner, ff)
+        ctx.has_out = out_w is not None
+        ctx.save_for_backward(x, xn, mean1, rstd1, qkv, attn, lse, x1, xn2, mean2, rstd2, z, h,
+                              n1_w, qkv_w, out_w, n2_w, l1_w, l2_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x, xn, mean1, rstd1, qkv, attn, lse, x1, xn2, mean2, rstd2, z, h,
+         n1_w, qkv_w, out_w, n2_w, l1_w, l2_w) = ctx.saved_tensors
+        cfg, seeds = ctx.cfg, ctx.seeds
+        m, p = cfg.mode, cfg.p
+        n, d, B, H, hd, S, inner, ff = ctx.dims
+        dev = x.device
+        dout = dout.contiguous()
+        # ---- feed-forward branch: out = x1 + Drop(W2 h + b2)
+        dz2 = ops.act_bwd(dout, dout, ACT_NONE, p, seeds[2]) if p > 0 else dout
+        dl2b = _zeros(d, dev)
+        ops.colsum(dz2, dl2b)
+        dz2p = m.split(dz2)
+        dl2w = m.wgrad(dz2p, m.split(h), n, d, ff)
+        dzp = m.dgrad(dz2p, n, d, l2_w, gelu_gate=z, dropout_p=p, seed=seeds[1])      # d(pre-GELU)
+        dl1b = _zeros(ff, dev)
+        ops.colsum(dzp, dl1b)
+        dzpp = m.split(dzp)
+        dl1w = m.wgrad(dzpp, m.split(xn2), n, ff, d)
+        dxn2 = m.dgrad(dzpp, n, ff, l1_w)
+        dn2w, dn2b = _zeros(d, dev), _zeros(d, dev)
+        dx1, _ = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2_w, dgamma=dn2w, dbeta=dn2b, dres=dout)
+        # ---- attention branch: x1 = x + Drop(Wo attn + bo)
+        if ctx.has_out:
+            dz1 = ops.act_bwd(dx1, dx1, ACT_NONE, p, seeds[0]) if p > 0 else dx1
+            dob = _zeros(d, dev)
+            ops.colsum(dz1, dob)
+            dz1p = m.split(dz1)
+            dow = m.wgrad(dz1p, m.split(attn), n, d, inner)
+            dattn = m.dgrad(dz1p, n, d, out_w)
+        else:
+            dow, dob, dattn = None, None, dx1
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], attn, dattn, lse, dqkv[:, :inner],
+                          dqkv[:, inner:2 * inner], dqkv[:, 2 * inner:], B, H, S, S, hd, hd ** -0.5, impl=cfg.attn_impl)
+        dqkvp = m.split(dqkv)
+        dqkvw = m.wgrad(dqkvp, m.split(xn), n, 3 * inner, d)
+        dxn = m.dgrad(dqkvp, n, 3 * inner, qkv_w)
+        dn1w, dn1b = _zeros(d, dev), _zeros(d, dev)
+        dx, _ = ops.layernorm_bwd(dxn, x, mean1, rstd1, n1_w, dgamma=dn1w, dbeta=dn1b, dres=dx1)
+        return (None, None, dx, dn1w, dn1b, dqkvw, dow, dob, dn2w, dn2b, dl1w, dl1b, dl2w, dl2b)
+
+
 class EmbedFn(torch.autograd.Function):
     """tokens[b, s] = LN(Drop((s == 0 ? cls[b] : feat[b, s-1]) + pe[s])) -> [B*S, d]."""
 

@@ -5,3 +5,4 @@ from .transformer import PositionalEncoding, SimpleTransformer  # noqa: F401
 from .frame_transformer import TransformerBase, FrameStream  # noqa: F401
 from .TPN import Reasoning, sum_group, SpatialPyramid  # noqa: F401
 from .fusion import CrossModalBlock, ExpertStream, FusionTransformer, DistillationTrainer  # noqa: F401
+from . import vit  # noqa: F401,E402

@@ -46,10 +46,23 @@ class FrameStream(LightningModule):
         self.img_mlp_head = nn.Sequential(nn.Linear(d, 512), nn.GELU(), nn.Linear(512, 128), nn.GELU(), nn.Linear(128, n_classes))
         self.running_labels, self.running_logits = [], []
 
-    def tokens(self, feats):
+    def tokens(self, feats, inject=None):
+        """feats (B, S, d) -> encoded (B, S, d).  ``inject`` (B, d): the other modality's CLS vector appended
+        as an extra token before the positional encoding, as FrameTransformer.img_step does in "sum" mode
+        (frame_transformer.py:225-226) -> encoded (B, S + 1, d)."""
         B, S, d = feats.shape
-        tok = self.position_encoder.tokens_forward(to_act(self.mode, feats).view(B * S, d), S)
+        x = to_act(self.mode, feats)
+        if inject is not None:
+            x = torch.cat((x, inject.to(x.dtype).unsqueeze(1)), dim=1).contiguous()
+            S += 1
+        tok = self.position_encoder.tokens_forward(x.view(B * S, d), S)
         return self.distil_transformer.tokens_forward(tok, B).view(B, S, d)
+
+    def sum_forward(self, feats, other_cls):
+        """FrameTransformer "sum" mode (frame_transformer.py:143-147,225-239): token injection, then
+        head(cls + last token)."""
+        seq = self.tokens(feats, inject=other_cls)
+        return self.head((seq[:, 0] + seq[:, -1]).contiguous())
 
     def head(self, cls):
         h = self.img_mlp_head

@@ -35,6 +35,8 @@ class PositionalEncoding(LightningModule):
 
     def tokens_forward(self, tokens, S):
         """Batch-major [B*S, d] entry used inside the package."""
+        if S > self.pe.shape[0]:
+            raise ValueError(f"sequence length {S} exceeds PositionalEncoding max_len {self.pe.shape[0]}")
         p = self.dropout.p if self.training else 0.0
         return PosEncFn.apply(tokens, self.pe.reshape(-1, self.pe.shape[-1])[:S].contiguous(), S, p)
 

@@ -224,9 +224,10 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, *, save_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, *, dgamma=None, dbeta=None, dbias=None, dropout_p=0.0, seed=0):
-    """Returns (dx, dz): dz is the dropout-masked branch gradient (dz is dx when dropout_p == 0)."""
-    _cuda(dy, x, mean, rstd, gamma, dgamma, dbeta, dbias)
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dgamma=None, dbeta=None, dbias=None, dropout_p=0.0, seed=0, dres=None):
+    """Returns (dx, dz): dz is the dropout-masked branch gradient (dz is dx when dropout_p == 0).
+    ``dres`` (pre-norm blocks) is added to dx."""
+    _cuda(dy, x, mean, rstd, gamma, dgamma, dbeta, dbias, dres)
     rows, d = x.shape
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if dropout_p > 0 else None
@@ -234,6 +235,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, dgamma=None, dbeta=None, dbias=No
     a.dy, a.x, a.mean, a.rstd, a.gamma, a.dx, a.dz = _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dz)
     a.dgamma, a.dbeta, a.dbias = _p(dgamma), _p(dbeta), _p(dbias)
     a.rows, a.d, a.seq_len, a.dtype, a.dropout_p, a.dropout_seed = rows, d, 0, _dt(x), dropout_p, seed
+    a.dres = _p(dres)
     capi.call("tvt_layernorm_bwd", a, _stream())
     return dx, (dz if dz is not None else dx)
 

@@ -140,7 +140,9 @@ TVT_API int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* args, void* stream);
 /* dx = LN'(dy); dgamma += sum_rows dy * xhat; dbeta += sum_rows dy (atomics: caller zero-fills).
  * dz (optional) = dropout-masked dx with the mask of the GEMM epilogue that produced the branch
  * (element index row * d + col), dbias (optional) += column sums of dz (of dx when dz is NULL).
- * Embed mode scatters the (dropout-masked) dx rows to dfeat [B, S-1, d] and dcls [B, d]. */
+ * Embed mode scatters the (dropout-masked) dx rows to dfeat [B, S-1, d] and dcls [B, d].
+ * dres (optional) is added to dx: in a pre-norm block (src/models/vit.py:71-75) x' = x + f(LN(x)), so
+ * dL/dx = dL/dx' + LN'(dL/dLN). */
 typedef struct {
   const void* dy;
   const void* x;      /* pre-LN input saved by the forward pass */
@@ -158,6 +160,7 @@ typedef struct {
   int32_t dtype;
   float dropout_p;
   uint64_t dropout_seed;
+  const void* dres;   /* optional [rows, d]: added to dx (the residual-path gradient of a pre-norm block) */
 } tvt_layernorm_bwd_args;
 TVT_API int tvt_layernorm_bwd(const tvt_layernorm_bwd_args* args, void* stream);
 

@@ -133,9 +133,17 @@ class FrameStream(nn.Module):
         self.img_mlp_head = nn.Sequential(nn.Linear(d, 512), nn.GELU(), nn.Linear(512, 128), nn.GELU(),
                                           nn.Linear(128, n_classes))
 
-    def tokens(self, feats):
-        data = self.position_encoder(feats.permute(1, 0, 2))
+    def tokens(self, feats, inject=None):
+        data = feats.permute(1, 0, 2)
+        if inject is not None:                      # frame_transformer.py:225-226 ("sum": cat the other modality's CLS)
+            data = torch.cat((data, inject.unsqueeze(0)))
+        data = self.position_encoder(data)
         return self.distil_transformer(data).permute(1, 0, 2)
+
+    def sum_forward(self, feats, other_cls):
+        """frame_transformer.py:143-147,237-239: (cls, last token) -> head(cls + last)."""
+        seq = self.tokens(feats, inject=other_cls)
+        return self.img_mlp_head(seq[:, 0] + seq[:, -1])
 
     def forward(self, feats):
         return self.img_mlp_head(self.tokens(feats)[:, 0])

@@ -201,6 +201,57 @@ def test_frame_stream_parity(api, precision):
     assert_close(mod.distil_transformer(x), ref.distil_transformer(x), TOL[precision], "TransformerBase.forward")
 
 
+@pytest.mark.parametrize("precision,b,n", [("fp32", 4, 50), ("bf16", 64, 50), ("bf16", 8, 197)])
+def test_vit_prenorm_transformer_parity(api, precision, b, n):
+    """src/models/vit.py Transformer at ViViT's defaults (dim 192, 3 heads x 64, GELU MLP 4x, pre-norm)."""
+    from oracle import param
+    torch.manual_seed(1130)
+    ref = param.VitTransformer(192, 2, 3, 64, 768).to(DEV)
+    mod = copy_state(api.vit.Transformer(192, 2, 3, 64, 768, precision=precision), ref).to(DEV)
+    gen = torch.Generator().manual_seed(1130)
+    x = torch.randn(b, n, 192, generator=gen).to(DEV)
+    w = torch.randn(b, n, 192, generator=gen).to(DEV)
+    (ref(x) * w).sum().backward()
+    out = mod(x)
+    (out.float() * w).sum().backward()
+    assert_close(out, ref(x), TOL[precision], "vit out")
+    grads_close(mod, ref, TOL[precision], "vit ", yard=_yardstick(ref, precision, lambda m: (_ac(lambda: m(x)).float() * w).sum()))
+
+
+def test_vit_matches_reference_golden(api):
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.pt"), weights_only=False)
+    torch.manual_seed(gold["seed"])
+    mod = api.vit.Transformer(32, 2, 2, 16, 64, precision="fp32").to(DEV).eval()   # same RNG stream as the reference
+    gen = torch.Generator().manual_seed(gold["seed"])
+    x = torch.randn(2, 5, 32, generator=gen).to(DEV)
+    assert_close(mod(x), gold["vit"]["out"], 1e-3, "vit golden")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_token_injection_fusion_parity(api, precision):
+    """FrameTransformer "sum" mode: the other modality's CLS vector joins the sequence as an extra token."""
+    from oracle import param
+    B = 4 if precision == "fp32" else 96
+    kw = dict(d=256, nhead=4, nhid=512, nlayers=2, dropout=0.0, seq_len=15, n_classes=19)
+    torch.manual_seed(1130)
+    ref = param.FrameStream(**kw).to(DEV)
+    mod = copy_state(api.FrameStream(precision=precision, **kw), ref).to(DEV)
+    gen = torch.Generator().manual_seed(1130)
+    feats = torch.randn(B, 14, 256, generator=gen).to(DEV)
+    other = torch.randn(B, 256, generator=gen).to(DEV)
+    y = _targets(B, 19, gen).to(DEV)
+    lr = torch.nn.functional.binary_cross_entropy_with_logits(ref.sum_forward(feats, other), y)
+    lr.backward()
+    logits = mod.sum_forward(feats, other)
+    from tvt_b200.functions import DistillLossFn
+    loss = DistillLossFn.apply(logits, None, y, 1.0, 0.0, 0.0, 1.0)[0]
+    loss.backward()
+    assert_close(logits, ref.sum_forward(feats, other), TOL[precision], "sum logits")
+    assert_close(loss, lr, TOL[precision], "loss")
+    grads_close(mod, ref, TOL[precision], "sum ", yard=_yardstick(
+        ref, precision, lambda m: torch.nn.functional.binary_cross_entropy_with_logits(_ac(lambda: m.sum_forward(feats, other)).float(), y)))
+
+
 def test_reasoning_and_spatial_pyramid_modules(api):
     from oracle import param
     torch.manual_seed(1130)
