@@ -78,6 +78,7 @@ __device__ __forceinline__ void mma_kk(uint32_t d_tmem, uint32_t a_smem, uint32_
 // work on the main tile.
 // smem: Q tile 16 KB | K sk_pad*128 | V sk_pad*128 | P ceil(sk_pad/64)*16 KB | barriers | tail scratch
 constexpr int kMaxTail = 8;
+constexpr int KC = 144;   // padded key capacity of one chunk: 128 + kMaxTail rounded up to 16
 
 __device__ __forceinline__ int main_tiles(int sq) {   // number of 128-row tensor-core tiles
   const int full = sq / 128, rem = sq - full * 128;
@@ -315,6 +316,255 @@ __global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant_
   }
   if (m_tiles == 0) __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------- forward, small
+// Sq <= 128 + kMaxTail AND Sk <= 128 + kMaxTail (every self-attention of the model family: S = 17 / 33 / 65 / 129).
+// Same roles as fwd_kernel, but sized for FOUR resident CTAs per SM (the kernel is a latency chain, so
+// residency is what buys throughput): the <= 8 tail KEYS are handled per thread on CUDA cores as well, which
+// keeps S at 128 TMEM columns (O then reuses S's first 64 columns: 128-column allocation), and P overwrites
+// the Q tile and the first 16 KB of the K tile once S has been computed (48 KB of tiles per CTA).
+__global__ void __launch_bounds__(kThreadsFwd, 4) fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                       // later: P block 0 (keys 0..63)
+  uint8_t* sK = sQ + 16384;                 // later: P block 1 (keys 64..127) over rows 0..127; tail key rows stay
+  uint8_t* sV = sK + KC * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KC * 128);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_q = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_o = bars + 3;
+  uint64_t* bar_tail = bars + 4;            // tail warp no longer needs the main K rows
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* tail_q = reinterpret_cast<float*>(bars + 8);   // [64]
+  float* tail_p = tail_q + HD;                          // [kMaxTail][KC]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = warp == 4 && lane == 0;
+  const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
+  const int n_rows = p.Sq < 128 ? p.Sq : 128;      // query rows on the tensor cores
+  const int tq_rows = p.Sq - n_rows;               // tail query rows (warp 5)
+  const int n_keys = p.Sk < 128 ? p.Sk : 128;      // keys on the tensor cores
+  const int tk = p.Sk - n_keys;                    // tail keys (per thread)
+  const int n_mma = (n_keys + 15) & ~15;
+  const float sl2 = p.scale * kLog2e;
+
+  if (issuer) {
+    mbar_init(smem_u32(bar_kv), 1);
+    mbar_init(smem_u32(bar_q), 1);
+    mbar_init(smem_u32(bar_s), 1);
+    mbar_init(smem_u32(bar_o), 1);
+    mbar_init(smem_u32(bar_tail), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+
+  if (issuer) {
+    mbar_arrive_expect_tx(smem_u32(bar_kv), 2 * p.sk_pad * 128);
+    for (int r = 0; r < p.sk_pad; r += p.kv_box) {
+      tma_load_2d(smem_u32(sK + r * 128), &tmK, smem_u32(bar_kv), h * HD, b * p.Sk + r);
+      tma_load_2d(smem_u32(sV + r * 128), &tmV, smem_u32(bar_kv), h * HD, b * p.Sk + r);
+    }
+    mbar_arrive_expect_tx(smem_u32(bar_q), 128 * 128);
+    tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq);
+    mbar_wait(smem_u32(bar_kv), 0);
+    mbar_wait(smem_u32(bar_q), 0);
+    tc_fence_after();
+    mma_kk(tmem_base, smem_u32(sQ), smem_u32(sK), n_mma);      // S = Q K^T over the main keys
+    tc_commit(smem_u32(bar_s));
+  }
+
+  if (warp == 5) {
+    // ---- tail query rows: all scores first (they read the main K rows that P will overwrite), then softmax / P V
+    if (tq_rows > 0) {
+      mbar_wait(smem_u32(bar_kv), 0);
+      for (int t = 0; t < tq_rows; ++t) {
+        const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + n_rows + t) * p.ldq + h * HD;
+        const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qrow + 2 * lane));
+        __syncwarp();
+        tail_q[2 * lane] = q2.x;
+        tail_q[2 * lane + 1] = q2.y;
+        __syncwarp();
+        for (int j = lane; j < p.Sk; j += 32) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float kf[8];
+            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(j, c)), kf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc += tail_q[c * 8 + i] * kf[i];
+          }
+          tail_p[t * KC + j] = acc;
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) mbar_arrive(smem_u32(bar_tail));
+    for (int t = 0; t < tq_rows; ++t) {
+      const int row = n_rows + t;
+      float mx = -INFINITY;
+      for (int j = lane; j < p.Sk; j += 32) mx = fmaxf(mx, tail_p[t * KC + j]);
+      mx = warp_max(mx);
+      float sum = 0.0f;
+      for (int j = lane; j < p.Sk; j += 32) {
+        const float e = exp2f((tail_p[t * KC + j] - mx) * sl2);
+        sum += e;
+        tail_p[t * KC + j] = e * drop_mul(p, bh, row, j);
+      }
+      sum = warp_sum(sum);
+      __syncwarp();
+      float o0 = 0.0f, o1 = 0.0f;
+      for (int j = 0; j < p.Sk; ++j) {
+        const float pj = tail_p[t * KC + j];
+        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sw_elem(sV, j, 2 * lane)));
+        o0 += pj * v2.x;
+        o1 += pj * v2.y;
+      }
+      const float inv = 1.0f / sum;
+      __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + row) * p.ldo + h * HD;
+      *reinterpret_cast<__nv_bfloat162*>(orow + 2 * lane) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+      if (lane == 0 && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + row] = mx * p.scale + __logf(sum);
+    }
+  }
+
+  const bool row_ok = warp < 4 && tid < n_rows;
+  const bool warp_ok = warp < 4 && warp * 32 < n_rows;
+  float mx = -INFINITY, sum = 0.0f;
+  float st[kMaxTail];        // raw scores, then probabilities, of the tail keys for this thread's row
+  if (warp_ok) {
+    mbar_wait(smem_u32(bar_s), 0);
+    tc_fence_after();
+    // tail-key scores on CUDA cores: q_i (own row of the Q tile) . k_t
+#pragma unroll
+    for (int t = 0; t < kMaxTail; ++t) {
+      st[t] = -INFINITY;
+      if (t < tk) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float qf[8], kf[8];
+          Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sQ + sw128(tid, c)), qf);
+          Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(128 + t, c)), kf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc += qf[i] * kf[i];
+        }
+        st[t] = acc;
+        mx = fmaxf(mx, acc);
+      }
+    }
+    for (int c0 = 0; c0 < n_mma; c0 += 32) {       // pass 1: row maximum over the main keys
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < n_keys) mx = fmaxf(mx, __uint_as_float(r[i]));
+    }
+    const float mxs = mx * sl2;
+    const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? tid : 0);
+#pragma unroll
+    for (int t = 0; t < kMaxTail; ++t) {
+      if (t < tk) {
+        const float e = exp2f(st[t] * sl2 - mxs);
+        sum += e;
+        st[t] = e * drop_mul(p, bh, row_ok ? tid : 0, 128 + t);
+      } else {
+        st[t] = 0.0f;
+      }
+    }
+    mbar_wait(smem_u32(bar_tail), 0);              // P block 1 is about to overwrite the main K rows
+    for (int c0 = 0; c0 < n_mma; c0 += 16) {       // pass 2: P (bf16) into the A-operand tiles
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
+      tmem_ld_wait();
+      uint32_t packed[8];
+      if (c0 + 16 <= n_keys && !p.dropout_thr16) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float e0 = exp2f(__uint_as_float(r[i]) * sl2 - mxs), e1 = exp2f(__uint_as_float(r[i + 1]) * sl2 - mxs);
+          sum += e0 + e1;
+          packed[i >> 1] = pack_bf16x2(e0, e1);
+        }
+      } else {
+        float m[16];
+        if (p.dropout_thr16) {
+          drop_mul16(p, rowkey, c0, m);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m[i] = 1.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float e0 = 0.0f, e1 = 0.0f;
+          if (c0 + i < n_keys) { e0 = exp2f(__uint_as_float(r[i]) * sl2 - mxs); sum += e0; e0 *= m[i]; }
+          if (c0 + i + 1 < n_keys) { e1 = exp2f(__uint_as_float(r[i + 1]) * sl2 - mxs); sum += e1; e1 *= m[i + 1]; }
+          packed[i >> 1] = pack_bf16x2(e0, e1);
+        }
+      }
+      const uint32_t blk = smem_u32(c0 < 64 ? sQ : sK);
+      const int ch = (c0 & 63) >> 3;
+      sts128(blk + sw128(tid, ch), packed[0], packed[1], packed[2], packed[3]);
+      sts128(blk + sw128(tid, ch + 1), packed[4], packed[5], packed[6], packed[7]);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (issuer) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, HD, false, true);
+    for (int k = 0; k < n_mma / 16; ++k) {     // O = P V over the main keys (accumulator reuses S's columns 0..63)
+      const uint32_t a = smem_u32(k < 4 ? sQ : sK) + (k & 3) * 32;
+      tc_mma_f16_ss(tmem_base, make_smem_desc_sw128(a, 16, 1024), make_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc, k > 0);
+    }
+    tc_commit(smem_u32(bar_o));
+  }
+  if (warp_ok) {
+    mbar_wait(smem_u32(bar_o), 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + (row_ok ? tid : 0)) * p.ldo + h * HD;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
+#pragma unroll
+        for (int t = 0; t < kMaxTail; ++t) {
+          if (t < tk) {
+            float vf[16];
+            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(128 + t, c0 >> 3)), *reinterpret_cast<float(*)[8]>(&vf[0]));
+            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(128 + t, (c0 >> 3) + 1)), *reinterpret_cast<float(*)[8]>(&vf[8]));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] += st[t] * vf[i];
+          }
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) pk[i >> 1] = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
+        *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    if (row_ok && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + tid] = mx * p.scale + __logf(sum);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------------- backward
@@ -561,7 +811,6 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const __grid_constant__ C
 // TMEM: S [0,144) | dP [160,304) | dK [320,384) | dV [384,448) | dQ [448,512)
 // smem: Q 16K | dO 16K | P 48K | dS 48K | K 18K | V 18K | barriers | D, lse | tail scratch
 constexpr int kThreadsBwd2 = 192;
-constexpr int KC = 144;
 
 __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -679,11 +928,8 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
       if (warp * 32 < n_main) {
         const float Di = sD[tid], Li = sL[tid];
         const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? tid : 0);
-        for (int c0 = 0; c0 < nk; c0 += 16) {
-          uint32_t rs[16], rp[16];
-          tmem_ld_32x32b_x16(tS + lane_addr + c0, rs);
-          tmem_ld_32x32b_x16(tdP + lane_addr + c0, rp);
-          tmem_ld_wait();
+        // 16 columns of P / dS from raw S / dP accumulators -> swizzled bf16 tiles
+        auto emit16 = [&](int c0, const uint32_t* rs, const uint32_t* rp) {
           float m[16];
           if (p.dropout_thr16) {
             drop_mul16(p, rowkey, k0 + c0, m);
@@ -715,6 +961,22 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
           sts128(smem_u32(sP) + blk + sw128(tid, ch + 1), pp[4], pp[5], pp[6], pp[7]);
           sts128(smem_u32(sdS) + blk + sw128(tid, ch), pd[0], pd[1], pd[2], pd[3]);
           sts128(smem_u32(sdS) + blk + sw128(tid, ch + 1), pd[4], pd[5], pd[6], pd[7]);
+        };
+        int c0 = 0;
+        for (; c0 + 32 <= nk; c0 += 32) {          // one TMEM round trip per 32 columns of S and dP
+          uint32_t rs[32], rp[32];
+          tmem_ld_32x32b_x32(tS + lane_addr + c0, rs);
+          tmem_ld_32x32b_x32(tdP + lane_addr + c0, rp);
+          tmem_ld_wait();
+          emit16(c0, rs, rp);
+          emit16(c0 + 16, rs + 16, rp + 16);
+        }
+        if (c0 < nk) {
+          uint32_t rs[16], rp[16];
+          tmem_ld_32x32b_x16(tS + lane_addr + c0, rs);
+          tmem_ld_32x32b_x16(tdP + lane_addr + c0, rp);
+          tmem_ld_wait();
+          emit16(c0, rs, rp);
         }
       } else {
         // query rows beyond the sequence feed the contraction of dV / dK: they must be zero
@@ -952,6 +1214,13 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
   if ((rc = make_map(&tq, a->q, a->batch * a->sq, w, a->ldq, 128)) != TVT_OK) return rc;
   if ((rc = make_map(&tk, a->k, a->batch * a->sk, w, a->ldk, p.kv_box)) != TVT_OK) return rc;
   if ((rc = make_map(&tv, a->v, a->batch * a->sk, w, a->ldv, p.kv_box)) != TVT_OK) return rc;
+  if (p.Sq <= 128 + kMaxTail && p.Sk <= 128 + kMaxTail) {
+    const int tq_rows = p.Sq > 128 ? p.Sq - 128 : 0;
+    const size_t bytes_s = 1024 + 16384 + 2 * (size_t)KC * 128 + 64 + (HD + (tq_rows > 0 ? tq_rows : 1) * KC) * 4;   // 4 CTAs / SM at S = 129
+    if ((rc = set_smem(fwd_small_kernel, bytes_s, "tvt_attention_fwd")) != TVT_OK) return rc;
+    fwd_small_kernel<<<p.B * p.H, kThreadsFwd, bytes_s, s>>>(tq, tk, tv, p);
+    return check_launch("tvt_attention_fwd");
+  }
   const int kv = ((p.sk_pad * 128) + 1023) & ~1023;
   const size_t bytes = 1024 + 16384 + 2 * (size_t)kv + (size_t)((p.sk_pad + 63) / 64) * 16384 + 64 + (HD + p.sk_pad) * 4;
   if ((rc = set_smem(fwd_kernel, bytes, "tvt_attention_fwd")) != TVT_OK) return rc;
