@@ -330,3 +330,74 @@ def test_training_mode_dropout_runs_and_is_consistent(api):
     mod.eval()
     a, b = mod([x])[0], mod([x])[0]
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["bf16"])
+def test_c5_shapes_distillation_parity(api, precision):
+    """The flagship shapes of BASELINE config 5 (128 frames -> S = 129 with a CUDA-core tail row / tail key,
+    d = 768, 12 heads of 64, ff = 3072, pyramid groups 2/3/4 over 128 frames, cross-attention over 258 keys)
+    at reduced depth (2 layers) and batch (32 clips): loss and every student gradient against the fp32 oracle."""
+    from oracle import param
+    B = 32
+    common = dict(d=768, nhead=12, nhid=3072, nlayers=2, dropout=0.0, batch_size=B, frames=128, n_classes=15)
+    torch.manual_seed(1130)
+    t_ref = param.FusionTransformer(in_dims=(2048, 1024, 128), fusion="cross", **common).to(DEV).eval()
+    s_ref = param.FusionTransformer(in_dims=(2048,), fusion="sum", pyramid=True, **common).to(DEV)
+    teacher = copy_state(api.FusionTransformer(in_dims=(2048, 1024, 128), fusion="cross", precision=precision, **common), t_ref).to(DEV)
+    student = copy_state(api.FusionTransformer(in_dims=(2048,), fusion="sum", pyramid=True, precision=precision, **common), s_ref).to(DEV)
+    with torch.no_grad():
+        for t in (t_ref, teacher):
+            t.mlp_head[1].bias[3] += 2.0
+    _no_dropout(t_ref, s_ref, teacher, student)
+    trainer = api.DistillationTrainer(teacher, student, temperature=2.0, alpha=1.0).train()
+    gen = torch.Generator().manual_seed(1130)
+    xs = [torch.relu(torch.randn(B, 128, D, generator=gen) * 0.5).to(DEV) if D > 128 else torch.randn(B, 128, D, generator=gen).to(DEV)
+          for D in (2048, 1024, 128)]
+    y = _targets(B, 15, gen).to(DEV)
+    with torch.no_grad():
+        t_logits, _ = t_ref(xs)
+        mine_t, _, _ = teacher(xs)
+    assert_close(mine_t, t_logits, TOL[precision], "teacher logits (cross-attention over 258 keys)")
+    s_logits, s_pyr = s_ref(xs[:1])
+    loss_r, _ = param.distill_loss(s_logits, t_logits, y, temperature=2.0, alpha=1.0, pyramid=s_pyr)
+    loss_r.backward()
+    loss = trainer.training_step({"experts": xs, "label": y})
+    loss.backward()
+    assert_close(loss, loss_r, TOL[precision], "C5-shape distillation loss")
+
+    def run(m):
+        lg, pr = _ac(lambda: m(xs[:1]))
+        return param.distill_loss(lg.float(), t_logits, y, temperature=2.0, alpha=1.0, pyramid=pr.float().clamp(1e-6, 1 - 1e-6))[0]
+
+    worst = grads_close(student, s_ref, TOL[precision], "C5 student ", yard=_yardstick(s_ref, precision, run))
+    print("C5-shape worst grad", worst)
+
+
+def test_full_size_properties(api):
+    """Size-independent properties at BASELINE config 5's FULL per-GPU size (256 clips x 128 frames, d = 768,
+    12 layers, 12 heads): clips are independent (permuting the batch permutes the logits), evaluation is
+    deterministic, and train mode with every dropout at 0 equals eval mode."""
+    kw = dict(in_dims=(2048,), d=768, nhead=12, nhid=3072, nlayers=12, dropout=0.0, batch_size=256, frames=128, n_classes=15,
+              fusion="sum", pyramid=True)
+    torch.manual_seed(1130)
+    mod = api.FusionTransformer(precision="bf16", **kw).to(DEV).eval()
+    with torch.no_grad():                      # identical CLS in every batch slot so that clips are exchangeable
+        mod.streams[0].cls.copy_(mod.streams[0].cls[:, :1].expand_as(mod.streams[0].cls))
+    gen = torch.Generator().manual_seed(1130)
+    x = torch.relu(torch.randn(256, 128, 2048, generator=gen) * 0.5).to(DEV)
+    perm = torch.randperm(256, generator=gen).to(DEV)
+    with torch.no_grad():
+        a, pa, _ = mod([x])
+        b, pb, _ = mod([x])
+        c, pc, _ = mod([x[perm]])
+        _no_dropout(mod)
+        mod.train()
+        d_, pd_, _ = mod([x])
+    # the encoder path is bit-deterministic; the pyramid's first Linear runs split-K with fp32 atomics, whose
+    # summation order varies from launch to launch: a few fp32 ulp, which the bf16 rounding of the hidden
+    # layer can turn into one bf16 ulp (0.4 %) of a hidden unit
+    close = lambda u, v: torch.allclose(u, v, rtol=0, atol=2e-3)
+    assert torch.equal(a, b) and close(pa, pb)                             # deterministic
+    assert torch.equal(c, a[perm]) and close(pc, pa[perm])                 # clip independence
+    assert torch.equal(d_, a) and close(pd_, pa)                           # dropout-free train == eval
+    assert torch.isfinite(a).all() and float(pa.min()) >= 0.0 and float(pa.max()) <= 1.0
