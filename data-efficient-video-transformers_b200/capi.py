@@ -107,6 +107,11 @@ class ActBwdArgs(C.Structure):
                 ("dropout_p", f32), ("dropout_seed", u64)]
 
 
+class OptimStepArgs(C.Structure):
+    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("p_hi", vp), ("p_lo", vp), ("n", i64), ("kind", i32), ("step", i32),
+                ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("momentum", f32), ("grad_scale", f32)]
+
+
 class HeadLinearFwdArgs(C.Structure):
     _fields_ = [("x", vp), ("w", vp), ("b", vp), ("y", vp), ("m", i64), ("k", i64), ("classes", i64), ("dtype", i32)]
 
@@ -138,6 +143,7 @@ ENTRY_POINTS = {
     "tvt_bias_act_fwd": BiasActArgs,
     "tvt_posenc_fwd": PosencArgs,
     "tvt_act_bwd": ActBwdArgs,
+    "tvt_optim_step": OptimStepArgs,
     "tvt_head_linear_fwd": HeadLinearFwdArgs,
     "tvt_head_linear_bwd": HeadLinearBwdArgs,
     "tvt_cls_sum_fwd": ClsSumArgs,

@@ -124,6 +124,69 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* dy, const T* yz, 
   }
 }
 
+// ---------------------------------------------------------------- optimizer step on a flat bucket
+struct OptParams {
+  float* p; const float* g; float* m; float* v; __nv_bfloat16* hi; __nv_bfloat16* lo; long long n; int kind; int first;
+  float lr, b1, b2, eps, wd, mom, gs, bc1_inv, bc2_rsqrt;
+};
+__global__ void __launch_bounds__(256) optim_kernel(const OptParams a) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < a.n; i += stride) {
+    float p[4], g[4], m[4], v[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool full = i + 4 <= a.n;
+    if (full) {
+      const float4 p4 = *reinterpret_cast<const float4*>(a.p + i), g4 = *reinterpret_cast<const float4*>(a.g + i);
+      const float4 m4 = *reinterpret_cast<const float4*>(a.m + i);
+      p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w; g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+      m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+      if (a.kind == 0) { const float4 v4 = *reinterpret_cast<const float4*>(a.v + i); v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w; }
+    } else {
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = i + j < a.n;
+        p[j] = ok ? a.p[i + j] : 0.f; g[j] = ok ? a.g[i + j] : 0.f; m[j] = ok ? a.m[i + j] : 0.f;
+        v[j] = ok && a.kind == 0 ? a.v[i + j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gj = g[j] * a.gs;
+      if (a.kind == 0) {
+        p[j] *= 1.0f - a.lr * a.wd;
+        m[j] = a.b1 * m[j] + (1.0f - a.b1) * gj;
+        v[j] = a.b2 * v[j] + (1.0f - a.b2) * gj * gj;
+        const float denom = sqrtf(v[j]) * a.bc2_rsqrt + a.eps;
+        p[j] -= a.lr * a.bc1_inv * (m[j] / denom);
+      } else {
+        gj += a.wd * p[j];
+        m[j] = a.first ? gj : a.mom * m[j] + gj;
+        p[j] -= a.lr * m[j];
+      }
+    }
+    if (full) {
+      *reinterpret_cast<float4*>(a.p + i) = make_float4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<float4*>(a.m + i) = make_float4(m[0], m[1], m[2], m[3]);
+      if (a.kind == 0) *reinterpret_cast<float4*>(a.v + i) = make_float4(v[0], v[1], v[2], v[3]);
+      if (a.hi) {
+        float h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(p[j]));
+        *reinterpret_cast<uint2*>(a.hi + i) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        if (a.lo) *reinterpret_cast<uint2*>(a.lo + i) = make_uint2(pack_bf16x2(p[0] - h[0], p[1] - h[1]), pack_bf16x2(p[2] - h[2], p[3] - h[3]));
+      }
+    } else {
+      for (int j = 0; j < 4 && i + j < a.n; ++j) {
+        a.p[i + j] = p[j]; a.m[i + j] = m[j];
+        if (a.kind == 0) a.v[i + j] = v[j];
+        if (a.hi) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(p[j]);
+          a.hi[i + j] = h;
+          if (a.lo) a.lo[i + j] = __float2bfloat16_rn(p[j] - __bfloat162float(h));
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- class-head linear
 template <typename T>
 __global__ void __launch_bounds__(128) head_fwd_kernel(const T* x, const float* w, const float* b, float* y, long long M, long long K, int C) {
@@ -293,6 +356,30 @@ extern "C" int tvt_act_bwd(const tvt_act_bwd_args* a, void* stream) {
   if (a->dtype == TVT_F32) misc::act_bwd_kernel<float><<<misc::grid1d(n / 4, 256), 256, 0, s>>>((const float*)a->dy, (const float*)a->y_or_z, (float*)a->dx, n, a->act, sc, thr, a->dropout_seed);
   else misc::act_bwd_kernel<__nv_bfloat16><<<misc::grid1d(n / 8, 256), 256, 0, s>>>((const __nv_bfloat16*)a->dy, (const __nv_bfloat16*)a->y_or_z, (__nv_bfloat16*)a->dx, n, a->act, sc, thr, a->dropout_seed);
   return check_launch("tvt_act_bwd");
+}
+
+extern "C" int tvt_optim_step(const tvt_optim_step_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->p && a->g && a->m, "tvt_optim_step: null pointer");
+  TVT_REQUIRE(a->kind == 0 || a->kind == 1, "tvt_optim_step: kind must be 0 (AdamW) or 1 (SGD)");
+  TVT_REQUIRE(a->kind == 1 || a->v, "tvt_optim_step: AdamW needs the second-moment buffer");
+  TVT_REQUIRE(a->n >= 0 && a->step >= 1, "tvt_optim_step: bad n / step");
+  TVT_REQUIRE(al16(a->p) && al16(a->g) && al16(a->m) && al16(a->v) && (reinterpret_cast<uintptr_t>(a->p_hi) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->p_lo) & 7) == 0,
+              "tvt_optim_step: buffers must be 16-byte aligned (bf16 planes 8-byte)");
+  TVT_REQUIRE(!a->p_lo || a->p_hi, "tvt_optim_step: p_lo without p_hi");
+  if (a->n == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  misc::OptParams q{};
+  q.p = a->p; q.g = a->g; q.m = a->m; q.v = a->v; q.hi = (__nv_bfloat16*)a->p_hi; q.lo = (__nv_bfloat16*)a->p_lo; q.n = a->n;
+  q.kind = a->kind; q.first = a->step == 1;
+  q.lr = a->lr; q.b1 = a->beta1; q.b2 = a->beta2; q.eps = a->eps; q.wd = a->weight_decay; q.mom = a->momentum;
+  q.gs = a->grad_scale == 0.0f ? 1.0f : a->grad_scale;
+  q.bc1_inv = 1.0f / (1.0f - powf(a->beta1, (float)a->step));
+  q.bc2_rsqrt = 1.0f / sqrtf(1.0f - powf(a->beta2, (float)a->step));
+  misc::optim_kernel<<<misc::grid1d((a->n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
+  return check_launch("tvt_optim_step");
 }
 
 extern "C" int tvt_head_linear_fwd(const tvt_head_linear_fwd_args* a, void* stream) {

@@ -31,16 +31,19 @@ class GradBucketReducer:
             self._make_bucket(cur)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
 
+    ALIGN = 8   # elements: every view starts 32-byte aligned (16 bytes for the bf16 planes laid out alike)
+
     def _make_bucket(self, ps):
-        n = sum(p.numel() for p in ps)
-        flat = torch.zeros(n, dtype=torch.float32, device=ps[0].device)
-        off = 0
-        b = {"flat": flat, "params": list(ps), "pending": len(ps), "handle": None}
+        offsets, n = [], 0
         for p in ps:
+            offsets.append(n)
+            n += -(-p.numel() // self.ALIGN) * self.ALIGN
+        flat = torch.zeros(n, dtype=torch.float32, device=ps[0].device)
+        b = {"flat": flat, "params": list(ps), "offsets": offsets, "pending": len(ps), "handle": None}
+        for p, off in zip(ps, offsets):
             if p.dtype != torch.float32:
                 raise TypeError("GradBucketReducer expects fp32 master parameters")
             p.grad = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
             self._index[id(p)] = b
         self.buckets.append(b)
 
@@ -59,7 +62,8 @@ class GradBucketReducer:
             b["handle"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def finish(self):
-        """Wait for every bucket, reduce the ones whose hooks never fired (unused params), average."""
+        """Wait for every bucket, reduce the ones whose hooks never fired (unused params), average
+        (unless ``average=False``: FlatOptimizer fuses the 1 / world scaling into its step kernel)."""
         for b in self.buckets:
             if self.world > 1:
                 if b["handle"] is None:

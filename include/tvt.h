@@ -348,6 +348,30 @@ typedef struct {
 } tvt_act_bwd_args;
 TVT_API int tvt_act_bwd(const tvt_act_bwd_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step on flat parameter / gradient buckets (the step right after
+ * backward).  Replaces torch.optim.AdamW / SGD of configure_optimizers (src/models/frame_transformer.py:123-134,
+ * src/models/transformer.py:58-64) with one pass over the bucket that also applies the data-parallel
+ * gradient averaging (grad_scale = 1 / world) and refreshes the bf16 operand planes of the weights, so the
+ * next step's GEMMs need no separate conversion pass.
+ *   kind 0 (AdamW): p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *                   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+ *   kind 1 (SGD):   g += wd * p;  buf = momentum * buf + g  (buf = g on the first step);  p -= lr * buf
+ * All arrays fp32 of n elements; `m` is the first-moment / momentum buffer, `v` unused for SGD. */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  void* p_hi;   /* optional bf16 copy of the updated parameters */
+  void* p_lo;   /* optional bf16 residual plane (fp32 parity mode) */
+  int64_t n;
+  int32_t kind;
+  int32_t step; /* 1-based */
+  float lr, beta1, beta2, eps, weight_decay, momentum, grad_scale;
+} tvt_optim_step_args;
+TVT_API int tvt_optim_step(const tvt_optim_step_args* args, void* stream);
+
 /* Skinny linear layer for class heads (N = classes <= 64, not tensor-core shaped):
  *   y[m, c] = sum_k x[m, k] * w[c, k] + b[c]      (mlp_head[1], src/models/transformer.py:54;
  *                                                   Reasoning's last Linear, src/models/TPN.py:97)
