@@ -17,6 +17,9 @@
 // are masked (the sequences here are 2^k + 1 tokens long: 17, 33, 65, 129).
 #include <cuda.h>
 
+#include <mutex>
+#include <set>
+
 #include "tvt_common.cuh"
 #include "tvt_ptx.cuh"
 
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant_
       for (; c0 + 32 <= p.sk_pad; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_S + lane_addr + c0, r);
-        tmem_ld_wait();
+        tmem_ld_wait_dep(r);
         if (c0 + 32 <= p.Sk) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant_
       if (c0 < p.sk_pad) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_S + lane_addr + c0, r);
-        tmem_ld_wait();
+        tmem_ld_wait_dep(r);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (c0 + i < p.Sk) mx = fmaxf(mx, __uint_as_float(r[i]));
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant_
       for (c0 = 0; c0 < p.sk_pad; c0 += 16) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_S + lane_addr + c0, r);
-        tmem_ld_wait();
+        tmem_ld_wait_dep(r);
         uint32_t packed[8];
         if (c0 + 16 <= p.Sk && !p.dropout_thr16) {
 #pragma unroll
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant_
       for (int c0 = 0; c0 < HD; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_O + lane_addr + c0, r);
-        tmem_ld_wait();
+        tmem_ld_wait_dep(r);
         if (row_ok) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant_
 // residency is what buys throughput): the <= 8 tail KEYS are handled per thread on CUDA cores as well, which
 // keeps S at 128 TMEM columns (O then reuses S's first 64 columns: 128-column allocation), and P overwrites
 // the Q tile and the first 16 KB of the K tile once S has been computed (48 KB of tiles per CTA).
-__global__ void __launch_bounds__(kThreadsFwd, 4) fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                                    const __grid_constant__ CUtensorMap tmV, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -336,10 +339,9 @@ __global__ void __launch_bounds__(kThreadsFwd, 4) fwd_small_kernel(const __grid_
   uint64_t* bar_q = bars + 1;
   uint64_t* bar_s = bars + 2;
   uint64_t* bar_o = bars + 3;
-  uint64_t* bar_tail = bars + 4;            // tail warp no longer needs the main K rows
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  float* tail_q = reinterpret_cast<float*>(bars + 8);   // [64]
-  float* tail_p = tail_q + HD;                          // [kMaxTail][KC]
+  float* tail_q = reinterpret_cast<float*>(bars + 8);   // [8 + 64] reduction scratch of the tail-row path
+  float* tail_p = tail_q + 8 + HD;                      // [KC] probabilities of the current tail row
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool issuer = warp == 4 && lane == 0;
@@ -356,7 +358,6 @@ __global__ void __launch_bounds__(kThreadsFwd, 4) fwd_small_kernel(const __grid_
     mbar_init(smem_u32(bar_q), 1);
     mbar_init(smem_u32(bar_s), 1);
     mbar_init(smem_u32(bar_o), 1);
-    mbar_init(smem_u32(bar_tail), 1);
     fence_mbar_init();
   }
   if (warp == 4) {
@@ -384,56 +385,55 @@ __global__ void __launch_bounds__(kThreadsFwd, 4) fwd_small_kernel(const __grid_
     tc_commit(smem_u32(bar_s));
   }
 
-  if (warp == 5) {
-    // ---- tail query rows: all scores first (they read the main K rows that P will overwrite), then softmax / P V
-    if (tq_rows > 0) {
-      mbar_wait(smem_u32(bar_kv), 0);
-      for (int t = 0; t < tq_rows; ++t) {
-        const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + n_rows + t) * p.ldq + h * HD;
-        const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qrow + 2 * lane));
-        __syncwarp();
-        tail_q[2 * lane] = q2.x;
-        tail_q[2 * lane + 1] = q2.y;
-        __syncwarp();
-        for (int j = lane; j < p.Sk; j += 32) {
-          float acc = 0.0f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float kf[8];
-            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(j, c)), kf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc += tail_q[c * 8 + i] * kf[i];
-          }
-          tail_p[t * KC + j] = acc;
-        }
-      }
-      __syncwarp();
-    }
-    if (lane == 0) mbar_arrive(smem_u32(bar_tail));
+  if (warp < 4 && tq_rows > 0) {
+    // ---- tail query rows, key-parallel on the 128 worker threads (thread j owns key j, and tail key 128 + j),
+    //      done while the tensor cores compute S for the main tile.  Spreading this over the four worker warps
+    //      (instead of a dedicated warp) keeps the four SM sub-partitions evenly loaded: every CTA's extra warp
+    //      would land on the same sub-partition, which became the bottleneck with four resident CTAs.
+    float* red = tail_q;                 // [8]   cross-warp max / sum
+    float* part = tail_q + 8;            // [64]  P V partial of the upper thread half
+    mbar_wait(smem_u32(bar_kv), 0);
     for (int t = 0; t < tq_rows; ++t) {
       const int row = n_rows + t;
-      float mx = -INFINITY;
-      for (int j = lane; j < p.Sk; j += 32) mx = fmaxf(mx, tail_p[t * KC + j]);
-      mx = warp_max(mx);
-      float sum = 0.0f;
-      for (int j = lane; j < p.Sk; j += 32) {
-        const float e = exp2f((tail_p[t * KC + j] - mx) * sl2);
-        sum += e;
-        tail_p[t * KC + j] = e * drop_mul(p, bh, row, j);
+      const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + row) * p.ldq + h * HD;
+      float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float qf[8], kf[8];
+        Vec16<__nv_bfloat16>::unpack(__ldg(reinterpret_cast<const uint4*>(qrow) + c), qf);
+        Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(tid, c)), kf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s0 += qf[i] * kf[i];
+        if (tid < tk) {
+          Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(128 + tid, c)), kf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s1 += qf[i] * kf[i];
+        }
       }
-      sum = warp_sum(sum);
-      __syncwarp();
-      float o0 = 0.0f, o1 = 0.0f;
-      for (int j = 0; j < p.Sk; ++j) {
-        const float pj = tail_p[t * KC + j];
-        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sw_elem(sV, j, 2 * lane)));
-        o0 += pj * v2.x;
-        o1 += pj * v2.y;
+      const bool k0ok = tid < n_keys, k1ok = tid < tk;
+      float mxt = warp_max(fmaxf(k0ok ? s0 : -INFINITY, k1ok ? s1 : -INFINITY));
+      if (lane == 0) red[warp] = mxt;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mxt = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+      const float e0 = k0ok ? exp2f((s0 - mxt) * sl2) : 0.0f, e1 = k1ok ? exp2f((s1 - mxt) * sl2) : 0.0f;
+      const float ws = warp_sum(e0 + e1);
+      if (lane == 0) red[4 + warp] = ws;
+      if (k0ok) tail_p[tid] = e0 * drop_mul(p, bh, row, tid);
+      if (k1ok) tail_p[128 + tid] = e1 * drop_mul(p, bh, row, 128 + tid);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float sumt = red[4] + red[5] + red[6] + red[7];
+      // P V: thread (c, half) sums the keys of its parity for output column c
+      const int c = tid & 63, half = tid >> 6;
+      float acc = 0.0f;
+      for (int j = half; j < p.Sk; j += 2) acc += tail_p[j] * __bfloat162float(*sw_elem(sV, j, c));
+      if (half == 1) part[c] = acc;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (half == 0) {
+        __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + row) * p.ldo + h * HD;
+        orow[c] = __float2bfloat16_rn((acc + part[c]) / sumt);
+        if (tid == 0 && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + row] = mxt * p.scale + __logf(sumt);
       }
-      const float inv = 1.0f / sum;
-      __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + row) * p.ldo + h * HD;
-      *reinterpret_cast<__nv_bfloat162*>(orow + 2 * lane) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
-      if (lane == 0 && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + row] = mx * p.scale + __logf(sum);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // scratch reused by the next tail row
     }
   }
 
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kThreadsFwd, 4) fwd_small_kernel(const __grid_
     for (int c0 = 0; c0 < n_mma; c0 += 32) {       // pass 1: row maximum over the main keys
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + c0, r);
-      tmem_ld_wait();
+      tmem_ld_wait_dep(r);
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (c0 + i < n_keys) mx = fmaxf(mx, __uint_as_float(r[i]));
@@ -482,11 +482,10 @@ __global__ void __launch_bounds__(kThreadsFwd, 4) fwd_small_kernel(const __grid_
         st[t] = 0.0f;
       }
     }
-    mbar_wait(smem_u32(bar_tail), 0);              // P block 1 is about to overwrite the main K rows
     for (int c0 = 0; c0 < n_mma; c0 += 16) {       // pass 2: P (bf16) into the A-operand tiles
       uint32_t r[16];
       tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
-      tmem_ld_wait();
+      tmem_ld_wait_dep(r);
       uint32_t packed[8];
       if (c0 + 16 <= n_keys && !p.dropout_thr16) {
 #pragma unroll
@@ -538,7 +537,7 @@ __global__ void __launch_bounds__(kThreadsFwd, 4) fwd_small_kernel(const __grid_
     for (int c0 = 0; c0 < HD; c0 += 16) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
-      tmem_ld_wait();
+      tmem_ld_wait_dep(r);
       if (row_ok) {
         float o[16];
 #pragma unroll
@@ -678,7 +677,7 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const __grid_constant__ C
             uint32_t rs[16], rp[16];
             tmem_ld_32x32b_x16(tS + lane_addr + c0, rs);
             tmem_ld_32x32b_x16(tdP + lane_addr + c0, rp);
-            tmem_ld_wait();
+            tmem_ld_wait_dep(rs, rp);
             uint32_t pp[8], pd[8];
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
@@ -754,7 +753,7 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const __grid_constant__ C
         uint32_t rk[16], rv[16];
         tmem_ld_32x32b_x16(tdK + lane_addr + c0, rk);
         tmem_ld_32x32b_x16(tdV + lane_addr + c0, rv);
-        tmem_ld_wait();
+        tmem_ld_wait_dep(rk, rv);
         if (key < p.Sk) {
           uint32_t a[8], c[8];
 #pragma unroll
@@ -783,7 +782,7 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const __grid_constant__ C
         for (int c0 = 0; c0 < HD; c0 += 16) {
           uint32_t r[16];
           tmem_ld_32x32b_x16(tdQ + mt * HD + lane_addr + c0, r);
-          tmem_ld_wait();
+          tmem_ld_wait_dep(r);
           if (row < p.Sq) {
             uint32_t a[8];
 #pragma unroll
@@ -967,7 +966,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
           uint32_t rs[32], rp[32];
           tmem_ld_32x32b_x32(tS + lane_addr + c0, rs);
           tmem_ld_32x32b_x32(tdP + lane_addr + c0, rp);
-          tmem_ld_wait();
+          tmem_ld_wait_dep(rs, rp);
           emit16(c0, rs, rp);
           emit16(c0 + 16, rs + 16, rp + 16);
         }
@@ -975,7 +974,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
           uint32_t rs[16], rp[16];
           tmem_ld_32x32b_x16(tS + lane_addr + c0, rs);
           tmem_ld_32x32b_x16(tdP + lane_addr + c0, rp);
-          tmem_ld_wait();
+          tmem_ld_wait_dep(rs, rp);
           emit16(c0, rs, rp);
         }
       } else {
@@ -1065,7 +1064,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
         uint32_t rk[16], rv[16];
         tmem_ld_32x32b_x16(tdK + lane_addr + c0, rk);
         tmem_ld_32x32b_x16(tdV + lane_addr + c0, rv);
-        tmem_ld_wait();
+        tmem_ld_wait_dep(rk, rv);
         if (ok) {
           float fk[16], fv[16];
 #pragma unroll
@@ -1128,7 +1127,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
     for (int c0 = 0; c0 < HD; c0 += 16) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(tdQ + lane_addr + c0, r);
-      tmem_ld_wait();
+      tmem_ld_wait_dep(r);
       if (tid < n_main) {
         uint32_t a[8];
 #pragma unroll
@@ -1186,13 +1185,23 @@ static int make_map(CUtensorMap* m, const void* ptr, long long rows, long long w
 
 bool supported(long long sq, long long sk, long long hd) { return hd == HD && sq <= 256 && sk <= 272 && sq >= 1 && sk >= 1; }
 
+// Opt a kernel in to the full 227 KB of dynamic shared memory, once per kernel per process.
 template <typename K>
 static int set_smem(K kern, size_t bytes, const char* what) {
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  static std::mutex mu;
+  static std::set<const void*> done;
+  if (bytes > 227 * 1024) {
+    set_last_error("%s: needs %zu bytes of shared memory", what, bytes);
+    return TVT_EINVAL;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count(reinterpret_cast<const void*>(kern))) return TVT_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) {
     set_last_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
     return TVT_ECUDA;
   }
+  done.insert(reinterpret_cast<const void*>(kern));
   return TVT_OK;
 }
 
@@ -1215,10 +1224,9 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
   if ((rc = make_map(&tk, a->k, a->batch * a->sk, w, a->ldk, p.kv_box)) != TVT_OK) return rc;
   if ((rc = make_map(&tv, a->v, a->batch * a->sk, w, a->ldv, p.kv_box)) != TVT_OK) return rc;
   if (p.Sq <= 128 + kMaxTail && p.Sk <= 128 + kMaxTail) {
-    const int tq_rows = p.Sq > 128 ? p.Sq - 128 : 0;
-    const size_t bytes_s = 1024 + 16384 + 2 * (size_t)KC * 128 + 64 + (HD + (tq_rows > 0 ? tq_rows : 1) * KC) * 4;   // 4 CTAs / SM at S = 129
+    const size_t bytes_s = 1024 + 16384 + 2 * (size_t)KC * 128 + 64 + (8 + HD + KC) * 4;   // 54 KB: 4 CTAs / SM
     if ((rc = set_smem(fwd_small_kernel, bytes_s, "tvt_attention_fwd")) != TVT_OK) return rc;
-    fwd_small_kernel<<<p.B * p.H, kThreadsFwd, bytes_s, s>>>(tq, tk, tv, p);
+    fwd_small_kernel<<<p.B * p.H, kThreads, bytes_s, s>>>(tq, tk, tv, p);
     return check_launch("tvt_attention_fwd");
   }
   const int kv = ((p.sk_pad * 128) + 1023) & ~1023;

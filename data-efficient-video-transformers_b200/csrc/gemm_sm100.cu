@@ -409,7 +409,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + tcol, r);
-        tmem_ld_wait();
+        tmem_ld_wait_dep(r);
         if (p.dbg == 1) continue;
         float v[32];
 #pragma unroll

@@ -173,6 +173,19 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+// two loads in flight, one wait
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&a)[N], uint32_t (&b)[N]) {
+  tmem_ld_wait_dep(a);
+  tmem_ld_wait_dep(b);   // second wait returns immediately; it only ties b's registers to the completion
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
