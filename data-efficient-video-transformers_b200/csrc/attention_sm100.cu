@@ -322,11 +322,13 @@ __global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------- forward, small
-// Sq <= 128 + kMaxTail AND Sk <= 128 + kMaxTail (every self-attention of the model family: S = 17 / 33 / 65 / 129).
+// Sq <= 128 + kMaxTail AND Sk <= 128 + kSmallTailKeys (every self-attention of the model family: S = 17 / 33 / 65 / 129).
 // Same roles as fwd_kernel, but sized for FOUR resident CTAs per SM (the kernel is a latency chain, so
 // residency is what buys throughput): the <= 8 tail KEYS are handled per thread on CUDA cores as well, which
 // keeps S at 128 TMEM columns (O then reuses S's first 64 columns: 128-column allocation), and P overwrites
 // the Q tile and the first 16 KB of the K tile once S has been computed (48 KB of tiles per CTA).
+constexpr int kSmallTailKeys = 2;   // per-thread tail keys are unrolled: keep the kernel small (S = 2^k + 1 needs 1)
+
 __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                                    const __grid_constant__ CUtensorMap tmV, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -392,15 +394,26 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     //      would land on the same sub-partition, which became the bottleneck with four resident CTAs.
     float* red = tail_q;                 // [8]   cross-warp max / sum
     float* part = tail_q + 8;            // [64]  P V partial of the upper thread half
+    // the tail query row comes straight from global memory: fetch it before waiting for the K / V tiles
+    uint4 qraw[8];
+    {
+      const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + n_rows) * p.ldq + h * HD;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) qraw[c] = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
+    }
     mbar_wait(smem_u32(bar_kv), 0);
     for (int t = 0; t < tq_rows; ++t) {
       const int row = n_rows + t;
-      const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + row) * p.ldq + h * HD;
+      if (t > 0) {
+        const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + row) * p.ldq + h * HD;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) qraw[c] = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
+      }
       float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float qf[8], kf[8];
-        Vec16<__nv_bfloat16>::unpack(__ldg(reinterpret_cast<const uint4*>(qrow) + c), qf);
+        Vec16<__nv_bfloat16>::unpack(qraw[c], qf);
         Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(tid, c)), kf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s0 += qf[i] * kf[i];
@@ -440,13 +453,13 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
   const bool row_ok = warp < 4 && tid < n_rows;
   const bool warp_ok = warp < 4 && warp * 32 < n_rows;
   float mx = -INFINITY, sum = 0.0f;
-  float st[kMaxTail];        // raw scores, then probabilities, of the tail keys for this thread's row
+  float st[kSmallTailKeys];  // raw scores, then probabilities, of the tail keys for this thread's row
   if (warp_ok) {
     mbar_wait(smem_u32(bar_s), 0);
     tc_fence_after();
     // tail-key scores on CUDA cores: q_i (own row of the Q tile) . k_t
 #pragma unroll
-    for (int t = 0; t < kMaxTail; ++t) {
+    for (int t = 0; t < kSmallTailKeys; ++t) {
       st[t] = -INFINITY;
       if (t < tk) {
         float acc = 0.0f;
@@ -473,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     const float mxs = mx * sl2;
     const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? tid : 0);
 #pragma unroll
-    for (int t = 0; t < kMaxTail; ++t) {
+    for (int t = 0; t < kSmallTailKeys; ++t) {
       if (t < tk) {
         const float e = exp2f(st[t] * sl2 - mxs);
         sum += e;
@@ -482,10 +495,8 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
         st[t] = 0.0f;
       }
     }
-    for (int c0 = 0; c0 < n_mma; c0 += 16) {       // pass 2: P (bf16) into the A-operand tiles
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
-      tmem_ld_wait_dep(r);
+    // pass 2: P (bf16) into the A-operand tiles, 32 columns per TMEM round trip
+    auto emit16 = [&](int c0, const uint32_t* r) {
       uint32_t packed[8];
       if (c0 + 16 <= n_keys && !p.dropout_thr16) {
 #pragma unroll
@@ -514,6 +525,13 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
       const int ch = (c0 & 63) >> 3;
       sts128(blk + sw128(tid, ch), packed[0], packed[1], packed[2], packed[3]);
       sts128(blk + sw128(tid, ch + 1), packed[4], packed[5], packed[6], packed[7]);
+    };
+#pragma unroll 1
+    for (int c0 = 0; c0 < n_mma; c0 += 16) {   // one copy of the body: the kernel is instruction-cache sensitive
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
+      tmem_ld_wait_dep(r);
+      emit16(c0, r);
     }
     fence_proxy_async_smem();
   }
@@ -533,30 +551,34 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     tc_fence_after();
     const float inv = 1.0f / sum;
     __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + (row_ok ? tid : 0)) * p.ldo + h * HD;
-#pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
+#pragma unroll 1
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + c0, r);
       tmem_ld_wait_dep(r);
       if (row_ok) {
-        float o[16];
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
 #pragma unroll
-        for (int t = 0; t < kMaxTail; ++t) {
-          if (t < tk) {
-            float vf[16];
-            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(128 + t, c0 >> 3)), *reinterpret_cast<float(*)[8]>(&vf[0]));
-            Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(128 + t, (c0 >> 3) + 1)), *reinterpret_cast<float(*)[8]>(&vf[8]));
+        for (int t = 0; t < kSmallTailKeys; ++t) {
+          if (t < tk) {          // tail keys: O_i += p_it * v_t
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] += st[t] * vf[i];
+            for (int g = 0; g < 4; ++g) {
+              float vf[8];
+              Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(128 + t, (c0 >> 3) + g)), vf);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[8 * g + i] += st[t] * vf[i];
+            }
           }
         }
-        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) pk[i >> 1] = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
-        *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        for (int g = 0; g < 4; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pk[i] = pack_bf16x2(o[8 * g + 2 * i] * inv, o[8 * g + 2 * i + 1] * inv);
+          *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       }
     }
     if (row_ok && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + tid] = mx * p.scale + __logf(sum);
@@ -961,16 +983,8 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
           sts128(smem_u32(sdS) + blk + sw128(tid, ch), pd[0], pd[1], pd[2], pd[3]);
           sts128(smem_u32(sdS) + blk + sw128(tid, ch + 1), pd[4], pd[5], pd[6], pd[7]);
         };
-        int c0 = 0;
-        for (; c0 + 32 <= nk; c0 += 32) {          // one TMEM round trip per 32 columns of S and dP
-          uint32_t rs[32], rp[32];
-          tmem_ld_32x32b_x32(tS + lane_addr + c0, rs);
-          tmem_ld_32x32b_x32(tdP + lane_addr + c0, rp);
-          tmem_ld_wait_dep(rs, rp);
-          emit16(c0, rs, rp);
-          emit16(c0 + 16, rs + 16, rp + 16);
-        }
-        if (c0 < nk) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < nk; c0 += 16) {      // one copy of the body: the kernel is instruction-cache sensitive
           uint32_t rs[16], rp[16];
           tmem_ld_32x32b_x16(tS + lane_addr + c0, rs);
           tmem_ld_32x32b_x16(tdP + lane_addr + c0, rp);
@@ -1059,7 +1073,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
       const bool ok = key < p.Sk;
       __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * p.lddk + h * HD;
       __nv_bfloat16* dvrow = p.dv + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * p.lddv + h * HD;
-#pragma unroll
+#pragma unroll 1
       for (int c0 = 0; c0 < HD; c0 += 16) {
         uint32_t rk[16], rv[16];
         tmem_ld_32x32b_x16(tdK + lane_addr + c0, rk);
@@ -1223,7 +1237,7 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
   if ((rc = make_map(&tq, a->q, a->batch * a->sq, w, a->ldq, 128)) != TVT_OK) return rc;
   if ((rc = make_map(&tk, a->k, a->batch * a->sk, w, a->ldk, p.kv_box)) != TVT_OK) return rc;
   if ((rc = make_map(&tv, a->v, a->batch * a->sk, w, a->ldv, p.kv_box)) != TVT_OK) return rc;
-  if (p.Sq <= 128 + kMaxTail && p.Sk <= 128 + kMaxTail) {
+  if (p.Sq <= 128 + kMaxTail && p.Sk <= 128 + kSmallTailKeys) {
     const size_t bytes_s = 1024 + 16384 + 2 * (size_t)KC * 128 + 64 + (8 + HD + KC) * 4;   // 54 KB: 4 CTAs / SM
     if ((rc = set_smem(fwd_small_kernel, bytes_s, "tvt_attention_fwd")) != TVT_OK) return rc;
     fwd_small_kernel<<<p.B * p.H, kThreads, bytes_s, s>>>(tq, tk, tv, p);
