@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(kThreads) bwd_kernel(const __grid_constant__ C
 //   if nk > 128: issuer recomputes dV / dK for keys 128..nk-1 from the third k-block (same TMEM columns)
 // TMEM: S [0,144) | dP [160,304) | dK [320,384) | dV [384,448) | dQ [448,512)
 // smem: Q 16K | dO 16K | P 48K | dS 48K | K 18K | V 18K | barriers | D, lse | tail scratch
-constexpr int kThreadsBwd2 = 192;
+constexpr int kThreadsBwd2 = 320;   // 8 worker warps (two threads per row), issue warp, tail warp
 
 __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -851,8 +851,8 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
   uint64_t* bar_g = bars + 3;       // dV, dK, dQ MMAs complete    (one phase per chunk)
   uint64_t* bar_t = bars + 4;       // tail-key dV, dK complete    (one phase per chunk that has tail keys)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  float* sD = reinterpret_cast<float*>(bars + 8);   // [128]
-  float* sL = sD + 128;                             // [128] lse * log2e
+  float* sDh = reinterpret_cast<float*>(bars + 8);  // [2][128] per-half partial D
+  float* sL = sDh + 256;                            // [128] lse * log2e
   float* tq = sL + 128;                             // [kMaxTail][64] tail query rows
   float* tdo = tq + kMaxTail * HD;                  // [kMaxTail][64] tail dO rows
   float* tdq = tdo + kMaxTail * HD;                 // [kMaxTail][64] tail dQ accumulators
@@ -861,7 +861,9 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
   float* tDL = tds + kMaxTail * KC;                 // [kMaxTail][2]  D_t, lse_t * log2e
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool issuer = warp == 4 && lane == 0;
+  const bool worker = warp < 8;
+  const int row = tid & 127, half = (tid >> 7) & 1;   // two worker threads per row: they split the columns
+  const bool issuer = warp == 8 && lane == 0;
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int n_main = p.Sq < 128 ? p.Sq : 128;       // valid rows of the tensor-core tile
   const int ntail = p.Sq - n_main;                  // rows handled by warp 5
@@ -873,7 +875,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
     mbar_init(smem_u32(bar_t), 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
@@ -890,25 +892,25 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
     tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq);
     tma_load_2d(smem_u32(sdO), &tmdO, smem_u32(bar_q), h * HD, b * p.Sq);
   }
-  if (warp < 4) {
-    // D_i = sum_c dO_ic O_ic and lse_i for the main rows, straight from global memory
+  if (worker) {
+    // D_i = sum_c dO_ic O_ic (each half sums 32 of the 64 columns) and lse_i for the main rows, from global memory
     float acc = 0.0f, l = 0.0f;
-    if (tid < n_main) {
-      const __nv_bfloat16* orow = p.o_in + (static_cast<long long>(b) * p.Sq + tid) * p.ldo + h * HD;
-      const __nv_bfloat16* drow = p.do_in + (static_cast<long long>(b) * p.Sq + tid) * p.lddo + h * HD;
+    if (row < n_main) {
+      const __nv_bfloat16* orow = p.o_in + (static_cast<long long>(b) * p.Sq + row) * p.ldo + h * HD + 32 * half;
+      const __nv_bfloat16* drow = p.do_in + (static_cast<long long>(b) * p.Sq + row) * p.lddo + h * HD + 32 * half;
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) {
+      for (int c = 0; c < 32; c += 8) {
         float a[8], d[8];
         Vec16<__nv_bfloat16>::load(orow + c, a);
         Vec16<__nv_bfloat16>::load(drow + c, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc += a[i] * d[i];
       }
-      l = p.lse[static_cast<long long>(bh) * p.Sq + tid] * kLog2e;
+      l = p.lse[static_cast<long long>(bh) * p.Sq + row] * kLog2e;
     }
-    sD[tid] = acc;
-    sL[tid] = l;
-  } else if (warp == 5) {
+    sDh[half * 128 + row] = acc;
+    sL[row] = l;
+  } else if (warp == 9) {
     for (int t = 0; t < ntail; ++t) {
       const long long grow = static_cast<long long>(b) * p.Sq + n_main + t;
       const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.q_in + grow * p.ldq + h * HD + 2 * lane));
@@ -942,13 +944,13 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
       mma_kk(tdP, smem_u32(sdO), smem_u32(sV), nk);    // dP = dO V^T
       tc_commit(smem_u32(bar_s));
     }
-    if (warp < 4) {
+    if (worker) {
       mbar_wait(smem_u32(bar_s), phase);
       tc_fence_after();
-      const bool row_ok = tid < n_main;
-      if (warp * 32 < n_main) {
-        const float Di = sD[tid], Li = sL[tid];
-        const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? tid : 0);
+      const bool row_ok = row < n_main;
+      if ((warp & 3) * 32 < n_main) {
+        const float Di = sDh[row] + sDh[128 + row], Li = sL[row];
+        const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? row : 0);
         // 16 columns of P / dS from raw S / dP accumulators -> swizzled bf16 tiles
         auto emit16 = [&](int c0, const uint32_t* rs, const uint32_t* rp) {
           float m[16];
@@ -978,13 +980,13 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
           }
           const uint32_t blk = (c0 >> 6) * 16384;
           const int ch = (c0 & 63) >> 3;
-          sts128(smem_u32(sP) + blk + sw128(tid, ch), pp[0], pp[1], pp[2], pp[3]);
-          sts128(smem_u32(sP) + blk + sw128(tid, ch + 1), pp[4], pp[5], pp[6], pp[7]);
-          sts128(smem_u32(sdS) + blk + sw128(tid, ch), pd[0], pd[1], pd[2], pd[3]);
-          sts128(smem_u32(sdS) + blk + sw128(tid, ch + 1), pd[4], pd[5], pd[6], pd[7]);
+          sts128(smem_u32(sP) + blk + sw128(row, ch), pp[0], pp[1], pp[2], pp[3]);
+          sts128(smem_u32(sP) + blk + sw128(row, ch + 1), pp[4], pp[5], pp[6], pp[7]);
+          sts128(smem_u32(sdS) + blk + sw128(row, ch), pd[0], pd[1], pd[2], pd[3]);
+          sts128(smem_u32(sdS) + blk + sw128(row, ch + 1), pd[4], pd[5], pd[6], pd[7]);
         };
 #pragma unroll 1
-        for (int c0 = 0; c0 < nk; c0 += 16) {      // one copy of the body: the kernel is instruction-cache sensitive
+        for (int c0 = 16 * half; c0 < nk; c0 += 32) {   // the two halves interleave 16-column chunks (one copy of the body)
           uint32_t rs[16], rp[16];
           tmem_ld_32x32b_x16(tS + lane_addr + c0, rs);
           tmem_ld_32x32b_x16(tdP + lane_addr + c0, rp);
@@ -993,14 +995,14 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
         }
       } else {
         // query rows beyond the sequence feed the contraction of dV / dK: they must be zero
-        for (int c0 = 0; c0 < nk; c0 += 8) {
-          const uint32_t off = (c0 >> 6) * 16384 + sw128(tid, (c0 & 63) >> 3);
+        for (int c0 = 8 * half; c0 < nk; c0 += 16) {
+          const uint32_t off = (c0 >> 6) * 16384 + sw128(row, (c0 & 63) >> 3);
           sts128(smem_u32(sP) + off, 0, 0, 0, 0);
           sts128(smem_u32(sdS) + off, 0, 0, 0, 0);
         }
       }
       fence_proxy_async_smem();
-    } else if (warp == 5 && ntail > 0) {
+    } else if (warp == 9 && ntail > 0) {
       // tail query rows against this key chunk (CUDA cores), K / V read from the swizzled smem tiles
       mbar_wait(smem_u32(bar_kv), phase);
       for (int t = 0; t < ntail; ++t) {
@@ -1067,47 +1069,39 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
       tc_commit(smem_u32(bar_g));
     }
     // drain dK / dV (thread == key row of the chunk), add the tail query rows' rank-1 terms
-    auto drain_keys = [&](int jbase) {
-      const int j = jbase + tid;                 // key index inside the chunk
+    auto drain_keys = [&](int jbase) {        // half 0 drains dK (+ dS_t q_t), half 1 drains dV (+ p_t dO_t)
+      const int j = jbase + row;                 // key index inside the chunk
       const int key = k0 + j;
       const bool ok = key < p.Sk;
-      __nv_bfloat16* dkrow = p.dk + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * p.lddk + h * HD;
-      __nv_bfloat16* dvrow = p.dv + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * p.lddv + h * HD;
+      __nv_bfloat16* grow = (half ? p.dv : p.dk) + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * (half ? p.lddv : p.lddk) + h * HD;
+      const float* tw = half ? tp : tds;         // per-key weight of the tail query rows
+      const float* tr = half ? tdo : tq;         // their row vectors
+      const uint32_t tacc = half ? tdV : tdK;
 #pragma unroll 1
-      for (int c0 = 0; c0 < HD; c0 += 16) {
-        uint32_t rk[16], rv[16];
-        tmem_ld_32x32b_x16(tdK + lane_addr + c0, rk);
-        tmem_ld_32x32b_x16(tdV + lane_addr + c0, rv);
-        tmem_ld_wait_dep(rk, rv);
+      for (int c0 = 0; c0 < HD; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tacc + lane_addr + c0, r);
+        tmem_ld_wait_dep(r);
         if (ok) {
-          float fk[16], fv[16];
+          float f[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { fk[i] = __uint_as_float(rk[i]); fv[i] = __uint_as_float(rv[i]); }
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
           for (int t = 0; t < ntail; ++t) {
-            const float dsj = tds[t * KC + j], pj = tp[t * KC + j];
+            const float wj = tw[t * KC + j];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              fk[i] += dsj * tq[t * HD + c0 + i];
-              fv[i] += pj * tdo[t * HD + c0 + i];
-            }
+            for (int i = 0; i < 32; ++i) f[i] += wj * tr[t * HD + c0 + i];
           }
-          uint32_t a[8], c[8];
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            a[i >> 1] = pack_bf16x2(fk[i], fk[i + 1]);
-            c[i >> 1] = pack_bf16x2(fv[i], fv[i + 1]);
-          }
-          *reinterpret_cast<uint4*>(dkrow + c0) = make_uint4(a[0], a[1], a[2], a[3]);
-          *reinterpret_cast<uint4*>(dkrow + c0 + 8) = make_uint4(a[4], a[5], a[6], a[7]);
-          *reinterpret_cast<uint4*>(dvrow + c0) = make_uint4(c[0], c[1], c[2], c[3]);
-          *reinterpret_cast<uint4*>(dvrow + c0 + 8) = make_uint4(c[4], c[5], c[6], c[7]);
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(grow + c0 + 8 * g) = make_uint4(pack_bf16x2(f[8 * g], f[8 * g + 1]), pack_bf16x2(f[8 * g + 2], f[8 * g + 3]),
+                                                                        pack_bf16x2(f[8 * g + 4], f[8 * g + 5]), pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
         }
       }
     };
-    if (warp < 4) {
+    if (worker) {
       mbar_wait(smem_u32(bar_g), phase);
       tc_fence_after();
-      if (k0 + warp * 32 < p.Sk) drain_keys(0);
+      if (k0 + (warp & 3) * 32 < p.Sk) drain_keys(0);
     }
     if (nk > 128) {
       tc_fence_before();
@@ -1123,10 +1117,10 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
         }
         tc_commit(smem_u32(bar_t));
       }
-      if (warp < 4) {
+      if (worker) {
         mbar_wait(smem_u32(bar_t), t_phase);
         tc_fence_after();
-        if (warp * 32 < nk - 128 && k0 + 128 + warp * 32 < p.Sk) drain_keys(128);
+        if ((warp & 3) * 32 < nk - 128 && k0 + 128 + (warp & 3) * 32 < p.Sk) drain_keys(128);
       }
       t_phase ^= 1;
     }
@@ -1135,22 +1129,19 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
     tc_fence_after();
   }
   // dQ: main rows from TMEM, tail rows from the CUDA-core accumulators
-  if (warp < 4 && warp * 32 < n_main) {
-    __nv_bfloat16* dqrow = p.dq + (static_cast<long long>(b) * p.Sq + (tid < n_main ? tid : 0)) * p.lddq + h * HD;
+  if (worker && (warp & 3) * 32 < n_main) {
+    __nv_bfloat16* dqrow = p.dq + (static_cast<long long>(b) * p.Sq + (row < n_main ? row : 0)) * p.lddq + h * HD + 32 * half;
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tdQ + lane_addr + 32 * half, r);
+    tmem_ld_wait_dep(r);
+    if (row < n_main) {
 #pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tdQ + lane_addr + c0, r);
-      tmem_ld_wait_dep(r);
-      if (tid < n_main) {
-        uint32_t a[8];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) a[i >> 1] = pack_bf16x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        *reinterpret_cast<uint4*>(dqrow + c0) = make_uint4(a[0], a[1], a[2], a[3]);
-        *reinterpret_cast<uint4*>(dqrow + c0 + 8) = make_uint4(a[4], a[5], a[6], a[7]);
-      }
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(dqrow + 8 * g) =
+            make_uint4(pack_bf16x2(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), pack_bf16x2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+                       pack_bf16x2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])), pack_bf16x2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     for (int t = 0; t < ntail; ++t) {
       __nv_bfloat16* dqrow = p.dq + (static_cast<long long>(b) * p.Sq + n_main + t) * p.lddq + h * HD;
       *reinterpret_cast<__nv_bfloat162*>(dqrow + 2 * lane) = __floats2bfloat162_rn(tdq[t * HD + 2 * lane], tdq[t * HD + 2 * lane + 1]);
@@ -1158,7 +1149,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------- host
@@ -1274,7 +1265,7 @@ int launch_bwd(const tvt_attention_bwd_args* a, cudaStream_t s) {
     if ((rc = make_map(&tq128, a->q, a->batch * a->sq, w, a->ldq, 128)) != TVT_OK) return rc;
     if ((rc = make_map(&tdo128, a->d_o, a->batch * a->sq, w, a->lddo, 128)) != TVT_OK) return rc;
     p.q_in = (const __nv_bfloat16*)a->q; p.ldq = a->ldq;
-    const size_t bytes2 = 1024 + 2 * 16384 + 6 * 16384 + 2 * (size_t)KC * 128 + 64 + 256 * 4 + (3 * kMaxTail * HD + 2 * kMaxTail * KC + 2 * kMaxTail) * 4;
+    const size_t bytes2 = 1024 + 2 * 16384 + 6 * 16384 + 2 * (size_t)KC * 128 + 64 + 384 * 4 + (3 * kMaxTail * HD + 2 * kMaxTail * KC + 2 * kMaxTail) * 4;
     if ((rc = set_smem(bwd2_kernel, bytes2, "tvt_attention_bwd")) != TVT_OK) return rc;
     bwd2_kernel<<<p.B * p.H, kThreadsBwd2, bytes2, s>>>(tq128, tk, tv, tdo128, p);
     return check_launch("tvt_attention_bwd");
