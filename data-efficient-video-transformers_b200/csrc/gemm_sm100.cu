@@ -23,9 +23,10 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each owning half the tile columns
-constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kThreads = 32 * kEpiWarps + 64;  // warps 0..7 epilogue (warp % 4 = TMEM lane quadrant), warp 8 TMA producer, warp 9 MMA issuer + TMEM owner
 constexpr int kStagePitch = 64;              // bytes per staged row: 32 bf16; 16 B chunks XOR-swizzled by (row >> 1) & 3
-constexpr int kEpiStageBytes = 32 * kStagePitch;  // per epilogue warp
+constexpr int kBiasSlab = 512;               // bytes: the bias of the (up to) 128 columns one epilogue warp owns
+constexpr int kEpiStageBytes = 32 * kStagePitch + kBiasSlab;  // per epilogue warp: staging rows, then the bias slab
 constexpr int kSmemLimit = 227 * 1024;
 
 struct Params {
@@ -37,15 +38,17 @@ struct Params {
   const void* relu_mask; int mask_f32; long long ld_mask;
   const void* gelu_gate; int gate_f32; long long ld_gate;
   float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+  unsigned drop_rk[kDropoutRounds];   // per-round keys of the dropout hash (host-computed: they are launch constants)
   void* out_preact; int preact_f32; long long ld_preact;
   float* out_f32; long long ld_f32; int atomic_out;
   __nv_bfloat16* out_bf16; __nv_bfloat16* out_bf16_lo; long long ld_bf16;
   unsigned mn_lbo, mn_sbo;  // MN-major descriptor strides (bring-up knob, see tvt_debug_set_mn_desc)
-  int dbg;                  // bring-up knob: 1 = epilogue drains TMEM only, 2 = no global stores
+  int dbg;                  // bring-up knob: low 2 bits 1 = epilogue drains TMEM only, 2 = no global stores; 4 = no main loop; 8 = no epilogue
 };
 
 static unsigned g_mn_lbo = BK * 128, g_mn_sbo = 1024;
 static int g_dbg = 0;
+static long long g_fast_fallbacks = 0;   // fast-path launches that had no exact-stage kernel (see tvt_gemm)
 
 template <int BN, int kPlanes>
 struct Cfg {
@@ -85,37 +88,62 @@ __device__ __forceinline__ void store8(void* base, int is_f32, long long off, co
 // ng = number of valid 8-column groups in the chunk (4 except in the last column block of a ragged N).
 // Every optional stage is ONE uniform branch around a straight-line block, which keeps the epilogue small
 // enough for the instruction cache (the first version, branching per 8-column group, was I$-bound).
-__device__ __forceinline__ void epilogue32(const Params& p, long long row, int col0, int ng, float (&v)[32],
-                                           const uint32_t (&mask_pk)[16], const uint32_t (&res_pk)[16], bool pre) {
-  if (p.atomic_out) {
-    float* dst = p.out_f32 + row * p.ld_f32 + col0;
+//
+// kEpi selects how much of this is compiled in.  The loop around it is instruction-cache bound when everything
+// is present (an 80 KB kernel against a 32 KB L1.5 I$), so the hot combinations get their own small kernels:
+//   kEpiFast   : alpha, bias, relu, bf16 relu mask, dropout, bf16 residual -> staged bf16 output
+//   kEpiAtomic : split-K fp32 red.add only
+//   kEpiGeneric: every stage (fp32 operands, pre-activation store, gelu, hi/lo planes, fp32 output ...)
+// kEpiFast + a stage mask (kStRelu ...) compiles exactly those stages in, unconditionally; plain kEpiFast checks
+// every stage at run time (the fallback for combinations that have no instantiation).
+enum { kEpiGeneric = 0, kEpiFast = 1, kEpiAtomic = 2, kEpiFastExact = 16 };
+enum { kStRelu = 1, kStMask = 2, kStDrop = 4, kStRes = 8 };
+__host__ __device__ constexpr bool is_fast(int kEpi) { return kEpi == kEpiFast || kEpi >= kEpiFastExact; }
+// does a fast kernel run stage st?  (compile-time constant for the exact kernels)
+template <int kEpi>
+__device__ __forceinline__ bool has_stage(int st, bool runtime) {
+  if constexpr (kEpi >= kEpiFastExact) return ((kEpi - kEpiFastExact) & st) != 0;
+  else return runtime;
+}
+
+__device__ __forceinline__ void epilogue_atomic(const Params& p, long long row, int col0, int ng, const float (&v)[32]) {
+  float* dst = p.out_f32 + row * p.ld_f32 + col0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (q < 2 * ng)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(v[4 * q] * p.alpha),
-                     "f"(v[4 * q + 1] * p.alpha), "f"(v[4 * q + 2] * p.alpha), "f"(v[4 * q + 3] * p.alpha)
-                     : "memory");
+  for (int q = 0; q < 8; ++q)
+    if (q < 2 * ng)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(v[4 * q] * p.alpha),
+                   "f"(v[4 * q + 1] * p.alpha), "f"(v[4 * q + 2] * p.alpha), "f"(v[4 * q + 3] * p.alpha)
+                   : "memory");
+}
+
+template <int kEpi>
+__device__ __forceinline__ void epilogue_stages(const Params& p, long long row, int col0, int ng, float (&v)[32],
+                                                const uint32_t (&mask_pk)[16], const uint32_t (&res_pk)[16], bool pre, uint32_t bias_s) {
+  if (kEpi == kEpiGeneric && p.atomic_out) {
+    epilogue_atomic(p, row, col0, ng, v);
     return;
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-  if (p.bias) {
+  if (p.bias) {   // broadcast reads of the warp's bias slab (global loads here serialised on the L2 latency)
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (q < 2 * ng) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
-        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-      }
+    for (int q = 0; q < 8; ++q) {
+      const uint4 b = lds128(bias_s + 16 * q);
+      v[4 * q] += __uint_as_float(b.x); v[4 * q + 1] += __uint_as_float(b.y);
+      v[4 * q + 2] += __uint_as_float(b.z); v[4 * q + 3] += __uint_as_float(b.w);
+    }
   }
-  if (p.out_preact) {
+  if constexpr (kEpi == kEpiGeneric) {
+    if (p.out_preact) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (g < ng) store8(p.out_preact, p.preact_f32, row * p.ld_preact + col0 + 8 * g, *reinterpret_cast<float(*)[8]>(&v[8 * g]));
+      for (int g = 0; g < 4; ++g)
+        if (g < ng) store8(p.out_preact, p.preact_f32, row * p.ld_preact + col0 + 8 * g, *reinterpret_cast<float(*)[8]>(&v[8 * g]));
+    }
   }
   if (p.act == TVT_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-  } else if (p.act == TVT_ACT_GELU) {
+  } else if (kEpi == kEpiGeneric && p.act == TVT_ACT_GELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
   }
@@ -127,7 +155,7 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
         v[2 * i] = m.x > 0.0f ? v[2 * i] : 0.0f;
         v[2 * i + 1] = m.y > 0.0f ? v[2 * i + 1] : 0.0f;
       }
-    } else {
+    } else if constexpr (kEpi == kEpiGeneric) {
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         if (g < ng) {
@@ -138,15 +166,17 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
         }
     }
   }
-  if (p.gelu_gate) {
+  if constexpr (kEpi == kEpiGeneric) {
+    if (p.gelu_gate) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (g < ng) {
-        float m[8];
-        load8(p.gelu_gate, p.gate_f32, row * p.ld_gate + col0 + 8 * g, m);
+      for (int g = 0; g < 4; ++g)
+        if (g < ng) {
+          float m[8];
+          load8(p.gelu_gate, p.gate_f32, row * p.ld_gate + col0 + 8 * g, m);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[8 * g + i] *= gelu_grad_f(m[i]);
-      }
+          for (int i = 0; i < 8; ++i) v[8 * g + i] *= gelu_grad_f(m[i]);
+        }
+    }
   }
   if (p.dropout_thr16) {
     const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;
@@ -165,7 +195,7 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
         v[2 * i] += m.x;
         v[2 * i + 1] += m.y;
       }
-    } else {
+    } else if constexpr (kEpi == kEpiGeneric) {
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         if (g < ng) {
@@ -176,6 +206,7 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
         }
     }
   }
+  if constexpr (kEpi != kEpiGeneric) return;
   if (p.out_f32) {
 #pragma unroll
     for (int g = 0; g < 4; ++g)
@@ -193,6 +224,74 @@ __device__ __forceinline__ void epilogue32(const Params& p, long long row, int c
       }
   }
   // the plain bf16 output (the hot path) is staged through shared memory by the caller
+}
+
+// 256-bit global accesses: one 32 B sector per lane, so "thread == row" epilogue traffic needs no transposition
+// through shared memory to be sector-efficient.
+__device__ __forceinline__ void ldg256(const void* ptr, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(ptr));
+}
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+// The hot-path epilogue (kEpiFast) on one 32-column chunk of one row: v = fma(acc, scale, bias'), relu, bf16
+// relu mask, dropout, bf16 residual, packed to bf16.  scale = alpha * dropout_scale and bias' = bias *
+// dropout_scale are folded by the caller (every stage before the residual is positively homogeneous), side[]
+// holds the row's 32 mask or residual values.  About 320 instructions with every stage on.
+template <int kEpi>
+__device__ __forceinline__ void epilogue_fast(const Params& p, float scale, uint32_t bias_s, uint32_t e4_lo, uint32_t e4_hi,
+                                              const uint32_t (&r)[32], const uint32_t (&side)[16], uint32_t (&out)[16]) {
+  float v[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 b = lds128(bias_s + 16 * q);   // broadcast read of the warp's bias slab
+    v[4 * q] = fmaf(__uint_as_float(r[4 * q]), scale, __uint_as_float(b.x));
+    v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), scale, __uint_as_float(b.y));
+    v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), scale, __uint_as_float(b.z));
+    v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), scale, __uint_as_float(b.w));
+  }
+  if (has_stage<kEpi>(kStRelu, p.act == TVT_ACT_RELU)) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  }
+  if (has_stage<kEpi>(kStMask, p.relu_mask != nullptr)) {   // keep where the bf16 mask value is > 0: integer tests on the packed halves
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[2 * i] = static_cast<int>(side[i] << 16) > 0 ? v[2 * i] : 0.0f;
+      v[2 * i + 1] = static_cast<int>(side[i]) >= 0x10000 ? v[2 * i + 1] : 0.0f;
+    }
+  }
+  if (has_stage<kEpi>(kStDrop, p.dropout_thr16 != 0)) {
+    const uint32_t thr_hi = p.dropout_thr16 << 16;   // (w >> 16) >= thr  <=>  w >= thr << 16
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t lo, hi;
+      dropout_words(p.drop_rk, e4_lo + q, e4_hi, lo, hi);
+      v[4 * q] = (lo << 16) >= thr_hi ? v[4 * q] : 0.0f;
+      v[4 * q + 1] = lo >= thr_hi ? v[4 * q + 1] : 0.0f;
+      v[4 * q + 2] = (hi << 16) >= thr_hi ? v[4 * q + 2] : 0.0f;
+      v[4 * q + 3] = hi >= thr_hi ? v[4 * q + 3] : 0.0f;
+    }
+  }
+  if (has_stage<kEpi>(kStRes, p.residual != nullptr)) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[2 * i] += __uint_as_float(side[i] << 16);
+      v[2 * i + 1] += __uint_as_float(side[i] & 0xFFFF0000u);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+}
+
+template <int kEpi>
+__device__ __forceinline__ void epilogue32(const Params& p, long long row, int col0, int ng, float (&v)[32],
+                                           const uint32_t (&mask_pk)[16], const uint32_t (&res_pk)[16], bool pre, uint32_t bias_s) {
+  if constexpr (kEpi == kEpiAtomic) epilogue_atomic(p, row, col0, ng, v);
+  else epilogue_stages<kEpi>(p, row, col0, ng, v, mask_pk, res_pk, pre, bias_s);
 }
 
 // Warp-cooperative fetch of a [32 rows x 32 bf16] block of a row-major matrix, in two halves so the global
@@ -229,7 +328,7 @@ __device__ __forceinline__ void fetch_land(const uint4 (&t)[4], uint32_t stage_a
   __syncwarp();
 }
 
-template <int BN, bool kAMN, bool kBMN, int kPlanes>
+template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -262,7 +361,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 2) {
+  if (warp == kEpiWarps + 1) {
     tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
     tmem_relinquish();
   }
@@ -276,7 +375,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int total = num_m * num_n * p.splits;
   const int kb_total = (p.K + BK - 1) / BK;
 
-  if (warp == 0) {
+  if (warp == kEpiWarps) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -288,6 +387,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb0 = static_cast<int>(static_cast<long long>(split) * kb_total / p.splits);
         const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (p.dbg & 4) break;
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_arrive_expect_tx(fb, C::kStageBytes);
@@ -317,7 +417,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kEpiWarps + 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, kAMN, kBMN);
       int stage = 0;
@@ -333,6 +433,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t d_tmem = tmem_base + as * BN;
         uint32_t accumulate = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (p.dbg & 4) break;
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           uint8_t* st = smem + stage * C::kStageBytes;
@@ -360,14 +461,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++as == C::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    const int ew = warp - 4;
+  } else {
+    const int ew = warp;
     const int quad = ew & 3;     // == warp % 4: the TMEM lane quadrant this warp may read
     const int half = ew >> 2;    // which half of the tile's columns this warp drains
     const uint32_t stage_addr = smem_u32(epi_stage + ew * kEpiStageBytes);
-    const bool staged = p.out_bf16 != nullptr && p.out_bf16_lo == nullptr && !p.atomic_out;
+    const bool staged = kEpi == kEpiGeneric && p.out_bf16 != nullptr && p.out_bf16_lo == nullptr && !p.atomic_out;
     int as = 0;
     uint32_t aphase = 0;
+    // kEpiFast state that lives across tiles (dead code in the other kernels)
+    const __nv_bfloat16* side_base = reinterpret_cast<const __nv_bfloat16*>(p.residual ? p.residual : p.relu_mask);
+    const bool has_side = has_stage<kEpi>(kStMask | kStRes, side_base != nullptr);
+    const long long ld_side = p.residual ? p.ld_residual : p.ld_mask;
+    const float dscale = has_stage<kEpi>(kStDrop, p.dropout_thr16 != 0) ? p.dropout_scale : 1.0f;
+    const float scale = p.alpha * dscale;
+    uint32_t side_a[16], side_b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) side_a[i] = side_b[i] = 0;
+    bool a_valid = false, bias_valid = false;
+    float4 bias_nx = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_bias = [&](int cb) {
+      const int c = cb + 4 * lane;
+      return (p.bias && c < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // L2-prefetch this warp's [32 x BN/2] slab of a tile's mask / residual (128 B lines)
+    auto prefetch_slab = [&](int wt) {
+      const long long prow0 = static_cast<long long>((wt / num_n) % num_m) * BM + quad * 32;
+      const int pcol = (wt % num_n) * BN + half * (BN / 2);
+#pragma unroll
+      for (int j = 0; j < BN / 128; ++j) {
+        const int line = lane + 32 * j;
+        const long long pr = prow0 + line / (BN / 128);
+        const int pc = pcol + (line % (BN / 128)) * 64;
+        if (pr < p.M && pc < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(side_base + pr * ld_side + pc));
+      }
+    };
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int n_blk = w % num_n;
       const int m_blk = (w / num_n) % num_m;
@@ -380,62 +508,145 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // operands of the fused stages that live in global memory are fetched coalesced (one warp = 32 rows) and
       // one chunk ahead: the first fetch is issued before waiting for the accumulator, the next one while the
       // current chunk is processed
-      const bool pre = !p.atomic_out;
-      const bool pre_res = pre && p.residual && !p.residual_f32;
-      const bool pre_mask = pre && p.relu_mask && !p.mask_f32;
-      const int colbase = n_blk * BN + half * (BN / 2);
-      uint4 pf[4];
-      if (pre_res) fetch_issue(p.residual, p.ld_residual, row0, colbase, p.M, p.N, lane, pf);
-      else if (pre_mask) fetch_issue(p.relu_mask, p.ld_mask, row0, colbase, p.M, p.N, lane, pf);
-      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int tcol = half * (BN / 2) + c * 32;   // column inside the tile
-        const int col0 = n_blk * BN + tcol;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t mask_pk[16], res_pk[16];
-        if (pre_res) {
-          fetch_land(pf, stage_addr, lane, res_pk);
-          if (c + 1 < BN / 64) fetch_issue(p.residual, p.ld_residual, row0, col0 + 32, p.M, p.N, lane, pf);
-          if (pre_mask) {   // both (not on the hot path): the mask is fetched in place
-            uint4 t[4];
-            fetch_issue(p.relu_mask, p.ld_mask, row0, col0, p.M, p.N, lane, t);
-            fetch_land(t, stage_addr, lane, mask_pk);
-          }
-        } else if (pre_mask) {
-          fetch_land(pf, stage_addr, lane, mask_pk);
-          if (c + 1 < BN / 64) fetch_issue(p.relu_mask, p.ld_mask, row0, col0 + 32, p.M, p.N, lane, pf);
+      if constexpr (is_fast(kEpi)) {
+        // thread == row throughout.  The row's mask / residual values arrive by 256-bit loads issued one chunk
+        // ahead into the other of two register buffers (across tile boundaries too; an L2 prefetch of the whole
+        // slab runs one tile ahead), the bf16 result leaves by 256-bit stores.
+        const int colbase = n_blk * BN + half * (BN / 2);
+        const __nv_bfloat16* side_row = side_base + row * ld_side;
+        const bool ld_ok = has_side && row < p.M && !(p.dbg & 16);
+        const int wn = w + static_cast<int>(gridDim.x);
+        const bool has_next = wn < total;
+        const long long row_n = static_cast<long long>((wn / num_n) % num_m) * BM + quad * 32 + lane;
+        const int colbase_n = (wn % num_n) * BN + half * (BN / 2);
+        if (has_side && !(p.dbg & 32)) {
+          if (w == static_cast<int>(blockIdx.x)) prefetch_slab(w);
+          if (has_next) prefetch_slab(wn);
         }
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + tcol, r);
-        tmem_ld_wait_dep(r);
-        if (p.dbg == 1) continue;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        const int ng = (p.N - col0) >= 32 ? 4 : (p.N - col0) >> 3;
-        if (row_ok) epilogue32(p, row, col0, ng, v, mask_pk, res_pk, pre);
-        if (staged) {
-          // thread == row: four 16 B chunks, XOR-swizzled so neither this write nor the read-back below conflicts
-          const uint32_t wbase = stage_addr + lane * kStagePitch;
-          const int sw = (lane >> 1) & 3;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            sts128(wbase + ((g ^ sw) << 4), pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
-                   pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
-          __syncwarp();
-          // coalesced write-out: 4 lanes x 16 B cover one staged row (64 B), 8 rows per pass
-          const int seg = lane & 3;
-          const int gcol = col0 + seg * 8;
-          __nv_bfloat16* gptr = p.out_bf16 + (row0 + (lane >> 2)) * p.ld_bf16 + gcol;
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int rr = ps * 8 + (lane >> 2);
-            const uint4 val = lds128(stage_addr + rr * kStagePitch + ((seg ^ ((rr >> 1) & 3)) << 4));
-            if (row0 + rr < p.M && gcol < p.N && kb1 > kb0 && p.dbg != 2) *reinterpret_cast<uint4*>(gptr + static_cast<long long>(ps) * 8 * p.ld_bf16) = val;
+        if (!a_valid && ld_ok && colbase < p.N) { ldg256(side_row + colbase, side_a); ldg256(side_row + colbase + 16, side_a + 8); }
+        if (4 * lane < BN / 2) {   // this warp's bias columns (pre-scaled; zeros without a bias) -> shared memory
+          if (!bias_valid) bias_nx = load_bias(colbase);
+          sts128(stage_addr + 32 * kStagePitch + 16 * lane, __float_as_uint(bias_nx.x * dscale), __float_as_uint(bias_nx.y * dscale),
+                 __float_as_uint(bias_nx.z * dscale), __float_as_uint(bias_nx.w * dscale));
+          if (has_next) bias_nx = load_bias(colbase_n);
+        }
+        bias_valid = has_next;
+        __syncwarp();
+        mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+        tc_fence_after();
+        // one chunk: start the TMEM load, start the side loads of the chunk after it, then finish this one
+        auto chunk = [&](int c, const uint32_t (&cur)[16], uint32_t (&nxt)[16], const __nv_bfloat16* nxt_ptr, bool nxt_ok) {
+          const int tcol = half * (BN / 2) + c * 32;   // column inside the tile
+          const int col0 = n_blk * BN + tcol;
+          const bool live = col0 < p.N && !(p.dbg & 8);   // warp-uniform
+          uint32_t r[32];
+          if (live) tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + tcol, r);
+          if (nxt_ok) { ldg256(nxt_ptr, nxt); ldg256(nxt_ptr + 16, nxt + 8); }
+          if (!live) return;
+          tmem_ld_wait_dep(r);
+          if ((p.dbg & 3) == 1) return;
+          const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;   // multiple of 8: + q never carries
+          uint32_t out[16];
+          epilogue_fast<kEpi>(p, scale, stage_addr + 32 * kStagePitch + c * 128, static_cast<uint32_t>(e4),
+                        static_cast<uint32_t>(e4 >> 32) ^ static_cast<uint32_t>(p.dropout_seed >> 32), r, cur, out);
+          if (row_ok && (p.dbg & 3) != 2) {
+            __nv_bfloat16* orow = p.out_bf16 + row * p.ld_bf16 + col0;
+            stg256(orow, out);
+            stg256(orow + 16, out + 8);
           }
-          __syncwarp();
+        };
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; c += 2) {
+          chunk(c, side_a, side_b, side_row + colbase + 32 * (c + 1), ld_ok && colbase + 32 * (c + 1) < p.N);
+          const bool last = c + 2 >= BN / 64;   // then the other buffer receives chunk 0 of this CTA's next tile
+          chunk(c + 1, side_b, side_a, last ? side_base + row_n * ld_side + colbase_n : side_row + colbase + 32 * (c + 2),
+                last ? (has_next && has_side && row_n < p.M && colbase_n < p.N && !(p.dbg & 16)) : (ld_ok && colbase + 32 * (c + 2) < p.N));
+        }
+        a_valid = has_next;
+        __syncwarp();   // every lane is done with the bias slab before the next tile overwrites it
+      } else {
+        const bool pre = kEpi == kEpiGeneric && !p.atomic_out;
+        const bool pre_res = pre && p.residual && !p.residual_f32;
+        const bool pre_mask = pre && p.relu_mask && !p.mask_f32;
+        const int colbase = n_blk * BN + half * (BN / 2);
+        uint4 pf[4];
+        if (pre_res) fetch_issue(p.residual, p.ld_residual, row0, colbase, p.M, p.N, lane, pf);
+        else if (pre_mask) fetch_issue(p.relu_mask, p.ld_mask, row0, colbase, p.M, p.N, lane, pf);
+        if constexpr (kEpi != kEpiAtomic) {
+          // while the main loop of this tile runs: pull the rest of the residual / mask slab into L2 (the register
+          // prefetch is only one chunk deep) and copy this warp's bias columns to shared memory
+          if (pre_res || pre_mask) {
+            const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(pre_res ? p.residual : p.relu_mask);
+            const long long ld = pre_res ? p.ld_residual : p.ld_mask;
+  #pragma unroll
+            for (int j = 0; j < BN / 128; ++j) {
+              const int line = lane + 32 * j;                       // 128 B lines of the [32 x BN/2] slab
+              const long long r = row0 + line / (BN / 128);
+              const int c = colbase + (line % (BN / 128)) * 64;
+              if (r < p.M && c < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + r * ld + c));
+            }
+          }
+          if (p.bias && !(kEpi == kEpiGeneric && p.atomic_out)) {
+            const int c = colbase + 4 * lane;
+            if (4 * lane < BN / 2) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+              sts128(stage_addr + 32 * kStagePitch + 16 * lane, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+            }
+            __syncwarp();
+          }
+        }
+        mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+        tc_fence_after();
+  #pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          if (p.dbg & 8) break;
+          const int tcol = half * (BN / 2) + c * 32;   // column inside the tile
+          const int col0 = n_blk * BN + tcol;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t mask_pk[16], res_pk[16];
+          if (pre_res) {
+            fetch_land(pf, stage_addr, lane, res_pk);
+            if (c + 1 < BN / 64) fetch_issue(p.residual, p.ld_residual, row0, col0 + 32, p.M, p.N, lane, pf);
+            if (pre_mask) {   // both (not on the hot path): the mask is fetched in place
+              uint4 t[4];
+              fetch_issue(p.relu_mask, p.ld_mask, row0, col0, p.M, p.N, lane, t);
+              fetch_land(t, stage_addr, lane, mask_pk);
+            }
+          } else if (pre_mask) {
+            fetch_land(pf, stage_addr, lane, mask_pk);
+            if (c + 1 < BN / 64) fetch_issue(p.relu_mask, p.ld_mask, row0, col0 + 32, p.M, p.N, lane, pf);
+          }
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + tcol, r);
+          tmem_ld_wait_dep(r);
+          if ((p.dbg & 3) == 1) continue;
+          float v[32];
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          const int ng = (p.N - col0) >= 32 ? 4 : (p.N - col0) >> 3;
+          if (row_ok) epilogue32<kEpi>(p, row, col0, ng, v, mask_pk, res_pk, pre, stage_addr + 32 * kStagePitch + c * 128);
+          if (staged) {
+            // thread == row: four 16 B chunks, XOR-swizzled so neither this write nor the read-back below conflicts
+            const uint32_t wbase = stage_addr + lane * kStagePitch;
+            const int sw = (lane >> 1) & 3;
+  #pragma unroll
+            for (int g = 0; g < 4; ++g)
+              sts128(wbase + ((g ^ sw) << 4), pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                     pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+            __syncwarp();
+            // coalesced write-out: 4 lanes x 16 B cover one staged row (64 B), 8 rows per pass
+            const int seg = lane & 3;
+            const int gcol = col0 + seg * 8;
+            __nv_bfloat16* gptr = p.out_bf16 + (row0 + (lane >> 2)) * p.ld_bf16 + gcol;
+  #pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const int rr = ps * 8 + (lane >> 2);
+              const uint4 val = lds128(stage_addr + rr * kStagePitch + ((seg ^ ((rr >> 1) & 3)) << 4));
+              if (row0 + rr < p.M && gcol < p.N && kb1 > kb0 && (p.dbg & 3) != 2) *reinterpret_cast<uint4*>(gptr + static_cast<long long>(ps) * 8 * p.ld_bf16) = val;
+            }
+            __syncwarp();
+          }
         }
       }
       tc_fence_before();
@@ -448,7 +659,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == kEpiWarps + 1) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -493,7 +704,7 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return TVT_OK;
 }
 
-template <int BN, bool kAMN, bool kBMN, int kPlanes>
+template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi>
 static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN, kPlanes>;
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
@@ -513,7 +724,7 @@ static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) 
     tmAlo = tmA;
     tmBlo = tmB;
   }
-  auto kern = gemm_kernel<BN, kAMN, kBMN, kPlanes>;
+  auto kern = gemm_kernel<BN, kAMN, kBMN, kPlanes, kEpi>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -530,12 +741,17 @@ static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) 
   return check_launch("tvt_gemm");
 }
 
-template <int BN, int kPlanes>
+template <int BN, int kPlanes, int kEpi>
 static int dispatch_major(const tvt_gemm_args* a, const Params& p, cudaStream_t s) {
-  if (!a->a_mn_major && !a->b_mn_major) return launch<BN, false, false, kPlanes>(a, p, s);
-  if (!a->a_mn_major && a->b_mn_major) return launch<BN, false, true, kPlanes>(a, p, s);
-  if (a->a_mn_major && a->b_mn_major) return launch<BN, true, true, kPlanes>(a, p, s);
-  return launch<BN, true, false, kPlanes>(a, p, s);
+  if (!a->a_mn_major && !a->b_mn_major) return launch<BN, false, false, kPlanes, kEpi>(a, p, s);
+  if (!a->a_mn_major && a->b_mn_major) return launch<BN, false, true, kPlanes, kEpi>(a, p, s);
+  if (a->a_mn_major && a->b_mn_major) return launch<BN, true, true, kPlanes, kEpi>(a, p, s);
+  return launch<BN, true, false, kPlanes, kEpi>(a, p, s);
+}
+
+template <int kPlanes, int kEpi>
+static int dispatch_width(bool narrow, const tvt_gemm_args* a, const Params& p, cudaStream_t s) {
+  return narrow ? dispatch_major<128, kPlanes, kEpi>(a, p, s) : dispatch_major<256, kPlanes, kEpi>(a, p, s);
 }
 
 }  // namespace gemm
@@ -548,6 +764,7 @@ extern "C" void tvt_debug_set_mn_desc(unsigned lbo, unsigned sbo) {
 }
 
 extern "C" void tvt_debug_set_epilogue(int mode) { tvt::gemm::g_dbg = mode; }
+extern "C" long long tvt_debug_gemm_fast_fallbacks() { return tvt::gemm::g_fast_fallbacks; }
 
 extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   using namespace tvt;
@@ -601,6 +818,7 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
     p.dropout_seed = a->dropout_seed;
+    for (int r = 0; r < kDropoutRounds; ++r) p.drop_rk[r] = static_cast<unsigned>(a->dropout_seed) + r * kDropoutWeyl;
   }
   p.out_preact = a->out_preact; p.preact_f32 = a->preact_dtype == TVT_F32; p.ld_preact = a->ld_preact;
   p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32; p.atomic_out = a->atomic_out;
@@ -619,6 +837,40 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   const long long c256 = ((w256 + nsm - 1) / nsm) * (kb_per * 512 + 3000);
   const long long c128 = ((w128 + nsm - 1) / nsm) * (kb_per * 400 + 1800);
   const bool narrow = a->n <= 128 || c128 < c256;
-  if (a->a_lo) return narrow ? gemm::dispatch_major<128, 2>(a, p, s) : gemm::dispatch_major<256, 2>(a, p, s);
-  return narrow ? gemm::dispatch_major<128, 1>(a, p, s) : gemm::dispatch_major<256, 1>(a, p, s);
+  // Epilogue kind: the small specialised kernels whenever the request fits them (see epilogue32); the fast one
+  // moves whole 32 B sectors per lane, so its row-major bf16 operands must be 32-byte aligned row by row
+  auto al32 = [](const void* ptr, long long ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0); };
+  const bool fast = !a->atomic_out && a->out_bf16 && !a->out_bf16_lo && !a->out_f32 && !a->out_preact && !a->gelu_gate &&
+                    (a->act == TVT_ACT_NONE || a->act == TVT_ACT_RELU) && !(a->residual && a->residual_dtype == TVT_F32) &&
+                    !(a->relu_mask && a->mask_dtype == TVT_F32) && !(a->residual && a->relu_mask) && a->n % 32 == 0 &&
+                    al32(a->out_bf16, a->ld_bf16) && al32(a->residual, a->ld_residual) && al32(a->relu_mask, a->ld_mask);
+  if (a->a_lo) {
+    if (a->atomic_out) return gemm::dispatch_width<2, gemm::kEpiAtomic>(narrow, a, p, s);
+    return gemm::dispatch_width<2, gemm::kEpiGeneric>(narrow, a, p, s);
+  }
+  if (a->atomic_out) return gemm::dispatch_width<1, gemm::kEpiAtomic>(narrow, a, p, s);
+  if (fast) {
+    // exact-stage kernels for the combinations the encoder layers launch (forward: both operands K-major; dgrad:
+    // B MN-major); anything else takes the fast kernel that checks its stages at run time
+    using namespace gemm;
+    const int st = (a->act == TVT_ACT_RELU ? kStRelu : 0) | (a->relu_mask ? kStMask : 0) | (a->dropout_p > 0.0f ? kStDrop : 0) | (a->residual ? kStRes : 0);
+#define TVT_FAST_CASE(AMN, BMN, ST)                                                                                   \
+  if (a->a_mn_major == AMN && a->b_mn_major == BMN && st == (ST))                                                     \
+    return narrow ? launch<128, AMN, BMN, 1, kEpiFastExact + (ST)>(a, p, s) : launch<256, AMN, BMN, 1, kEpiFastExact + (ST)>(a, p, s);
+    TVT_FAST_CASE(false, false, 0)
+    TVT_FAST_CASE(false, false, kStRelu)
+    TVT_FAST_CASE(false, false, kStRelu | kStDrop)
+    TVT_FAST_CASE(false, false, kStRes)
+    TVT_FAST_CASE(false, false, kStDrop | kStRes)
+    TVT_FAST_CASE(false, false, kStDrop)
+    TVT_FAST_CASE(false, true, 0)
+    TVT_FAST_CASE(false, true, kStRes)
+    TVT_FAST_CASE(false, true, kStMask)
+    TVT_FAST_CASE(false, true, kStMask | kStDrop)
+    TVT_FAST_CASE(false, true, kStDrop)
+#undef TVT_FAST_CASE
+    ++g_fast_fallbacks;
+    return dispatch_width<1, kEpiFast>(narrow, a, p, s);
+  }
+  return gemm::dispatch_width<1, gemm::kEpiGeneric>(narrow, a, p, s);
 }

@@ -124,18 +124,27 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // the fewest whose keep-bits show no measurable lag / cross-seed correlation on 2^21-element streams, see
 // DESIGN.md) yields 64 bits = 4 independent 16-bit lanes for 4 consecutive elements; ~15 integer
 // instructions per 4 elements.
-__device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t elem_div4) {
-  uint32_t R = static_cast<uint32_t>(elem_div4);
-  uint32_t L = static_cast<uint32_t>(elem_div4 >> 32) ^ static_cast<uint32_t>(seed >> 32);
-  uint32_t k = static_cast<uint32_t>(seed);
+constexpr int kDropoutRounds = 5;
+constexpr uint32_t kDropoutMul = 0xD256D193u, kDropoutWeyl = 0x9E3779B9u;
+// Same hash with the per-round keys (seed_lo + r * kDropoutWeyl) and the starting words handed in, for callers
+// that hoist them out of a hot loop; L0 = high word of elem_div4 ^ high word of the seed.
+__device__ __forceinline__ void dropout_words(const uint32_t (&rk)[kDropoutRounds], uint32_t R, uint32_t L, uint32_t& w_lo, uint32_t& w_hi) {
 #pragma unroll
-  for (int r = 0; r < 5; ++r) {
-    const uint64_t m = static_cast<uint64_t>(R) * 0xD256D193ull;
-    R = static_cast<uint32_t>(m >> 32) ^ k ^ L;
+  for (int r = 0; r < kDropoutRounds; ++r) {
+    const uint64_t m = static_cast<uint64_t>(R) * kDropoutMul;
+    R = static_cast<uint32_t>(m >> 32) ^ rk[r] ^ L;
     L = static_cast<uint32_t>(m);
-    k += 0x9E3779B9u;
   }
-  return (static_cast<uint64_t>(L) << 32) | R;
+  w_lo = R;   // lanes 0, 1
+  w_hi = L;   // lanes 2, 3
+}
+__device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t elem_div4) {
+  uint32_t rk[kDropoutRounds];
+#pragma unroll
+  for (int r = 0; r < kDropoutRounds; ++r) rk[r] = static_cast<uint32_t>(seed) + r * kDropoutWeyl;
+  uint32_t lo, hi;
+  dropout_words(rk, static_cast<uint32_t>(elem_div4), static_cast<uint32_t>(elem_div4 >> 32) ^ static_cast<uint32_t>(seed >> 32), lo, hi);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 // Lane i (0..3) survives dropout when its 16 random bits are >= thr16 (= p * 65536).
 __device__ __forceinline__ bool dropout_keep_lane(uint64_t bits, int i, uint32_t thr16) {

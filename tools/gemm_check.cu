@@ -80,7 +80,7 @@ static int run_case(const Case& c, bool verbose) {
   return bad ? 1 : 0;
 }
 
-static void bench(int M, int N, int K, int amn, int bmn, int planes, int splits) {
+static void bench(int M, int N, int K, int amn, int bmn, int planes, int splits, int epi = 0) {
   const long long lda = amn ? M : K, ldb = bmn ? N : K;
   const size_t na = (size_t)(amn ? K : M) * lda, nb = (size_t)(bmn ? K : N) * ldb;
   __nv_bfloat16 *dA, *dB, *dO; float* dF;
@@ -90,6 +90,17 @@ static void bench(int M, int N, int K, int amn, int bmn, int planes, int splits)
   g.a = dA; g.b = dB; if (planes == 2) { g.a_lo = dA; g.b_lo = dB; }
   g.m = M; g.n = N; g.k = K; g.lda = lda; g.ldb = ldb; g.a_mn_major = amn; g.b_mn_major = bmn; g.splits = splits; g.alpha = 1.0f;
   if (splits > 1) { g.out_f32 = dF; g.ld_f32 = N; g.atomic_out = 1; } else { g.out_bf16 = dO; g.ld_bf16 = N; }
+  // epi: 1 = bias + relu + dropout, 2 = bias + bf16 residual, 3 = bf16 relu mask + dropout, 4 = bias + dropout + residual
+  __nv_bfloat16* dR = nullptr; float* dBias = nullptr;
+  if (epi) {
+    CK(cudaMalloc(&dR, (size_t)M * N * 2)); CK(cudaMemset(dR, 0x3c, (size_t)M * N * 2));
+    CK(cudaMalloc(&dBias, (size_t)N * 4)); CK(cudaMemset(dBias, 0, (size_t)N * 4));
+    if (epi != 3) g.bias = dBias;
+    if (epi == 1) g.act = TVT_ACT_RELU;
+    if (epi == 1 || epi == 3 || epi == 4) { g.dropout_p = 0.5f; g.dropout_seed = 7; }
+    if (epi == 2 || epi == 4) { g.residual = dR; g.ld_residual = N; g.residual_dtype = TVT_BF16; }
+    if (epi == 3) { g.relu_mask = dR; g.ld_mask = N; g.mask_dtype = TVT_BF16; }
+  }
   for (int i = 0; i < 3; ++i) tvt_gemm(&g, 0);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int iters = 20;
@@ -97,17 +108,17 @@ static void bench(int M, int N, int K, int amn, int bmn, int planes, int splits)
   for (int i = 0; i < iters; ++i) tvt_gemm(&g, 0);
   cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
-  printf("bench m=%d n=%d k=%d A:%s B:%s planes=%d splits=%d: %.3f ms  %.1f TFLOP/s\n", M, N, K, amn ? "MN" : "K", bmn ? "MN" : "K", planes, splits, ms,
+  printf("bench m=%d n=%d k=%d A:%s B:%s planes=%d splits=%d epi=%d: %.3f ms  %.1f TFLOP/s\n", M, N, K, amn ? "MN" : "K", bmn ? "MN" : "K", planes, splits, epi, ms,
          2.0 * M * N * K * (planes == 2 ? 3 : 1) / ms * 1e-9);
-  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dF);
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dF); cudaFree(dR); cudaFree(dBias);
 }
 
 int main(int argc, char** argv) {
   if (tvt_device_check() != 0) { printf("device check failed: %s\n", tvt_last_error()); return 1; }
   if (getenv("TVT_EPI_DBG")) tvt_debug_set_epilogue(atoi(getenv("TVT_EPI_DBG")));
-  if (argc >= 5 && !strcmp(argv[1], "one")) {   // gemm_check one M N K [amn bmn planes splits]: a single shape, for ncu
+  if (argc >= 5 && !strcmp(argv[1], "one")) {   // gemm_check one M N K [amn bmn planes splits epi]: a single shape, for ncu
     bench(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 0, argc > 6 ? atoi(argv[6]) : 0,
-          argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 1);
+          argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 1, argc > 9 ? atoi(argv[9]) : 0);
     return 0;
   }
   int fails = 0;
