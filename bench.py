@@ -385,6 +385,12 @@ def main():
             for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"]):
                 tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] else 0.0
                 f.write(f"{k:28s} calls={v['calls']:5d}  ms={v['ms']:9.3f}  share={v['ms'] / total_ms:6.3f}  TFLOP/s={tf:8.1f}\n")
+            f.write("# per launch shape (GEMM stage letters: b bias, R relu, m relu mask, d dropout, r residual, F fp32 out, L hi/lo planes)\n")
+            for (k, det), v in sorted(capi.last_profile_detail.items(), key=lambda kv: -kv[1]["ms"]):
+                if not det:
+                    continue
+                tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] else 0.0
+                f.write(f"  {k:20s} {det:62s} calls={v['calls']:4d}  ms={v['ms']:8.3f}  us/call={v['ms'] * 1e3 / v['calls']:8.1f}  TFLOP/s={tf:7.1f}\n")
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -192,6 +192,21 @@ def _flops(name, a):
     return 0.0
 
 
+def _detail(name, a):
+    """Shape key of a launch for the per-shape table of profile_step()."""
+    if name == "tvt_gemm":
+        st = "".join(t for t, on in (("b", a.bias), ("R", a.act == 1), ("G", a.act == 2), ("m", a.relu_mask), ("g", a.gelu_gate),
+                                      ("d", a.dropout_p > 0), ("r", a.residual), ("p", a.out_preact), ("F", a.out_f32), ("L", a.out_bf16_lo)) if on)
+        return (f"{a.m}x{a.n}x{a.k} A:{'MN' if a.a_mn_major else 'K'} B:{'MN' if a.b_mn_major else 'K'} "
+                f"planes={2 if a.a_lo else 1} splits={a.splits} [{st}]")
+    if name in ("tvt_attention_fwd", "tvt_attention_bwd"):
+        return f"B={a.batch} H={a.heads} Sq={a.sq} Sk={a.sk} p={a.dropout_p:.2f}"
+    return ""
+
+
+last_profile_detail = {}  # {(entry point, shape key): {ms, flops, calls}} of the latest profile_step()
+
+
 def call(name, args, stream):
     """Invoke entry point ``name`` with a filled args Structure on cudaStream_t ``stream`` (int)."""
     global launches
@@ -204,7 +219,7 @@ def call(name, args, stream):
         e0.record()
         rc = fn(C.byref(args), vp(stream))
         e1.record()
-        _profile.append((name, e0, e1, _flops(name, args)))
+        _profile.append((name, e0, e1, _flops(name, args), _detail(name, args)))
     if rc != 0:
         raise TvtError(f"{name} failed with status {rc}: {last_error()}")
     launches += 1
@@ -220,11 +235,14 @@ def profile_step(fn):
         fn()
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, fl in _profile:
-            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "calls": 0})
-            d["ms"] += e0.elapsed_time(e1)
-            d["flops"] += fl
-            d["calls"] += 1
+        last_profile_detail.clear()
+        for name, e0, e1, fl, det in _profile:
+            ms = e0.elapsed_time(e1)
+            for d in (out.setdefault(name, {"ms": 0.0, "flops": 0.0, "calls": 0}),
+                      last_profile_detail.setdefault((name, det), {"ms": 0.0, "flops": 0.0, "calls": 0})):
+                d["ms"] += ms
+                d["flops"] += fl
+                d["calls"] += 1
         return out
     finally:
         _profile = None

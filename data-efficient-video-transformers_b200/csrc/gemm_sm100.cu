@@ -23,10 +23,11 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each owning half the tile columns
-constexpr int kThreads = 32 * kEpiWarps + 64;  // warps 0..7 epilogue (warp % 4 = TMEM lane quadrant), warp 8 TMA producer, warp 9 MMA issuer + TMEM owner
+constexpr int kThreads = 32 * kEpiWarps + 96;  // warps 0..7 epilogue (warp % 4 = TMEM lane quadrant), 8 TMA producer, 9 MMA issuer + TMEM owner, 10 side-operand producer
+constexpr int kSideSlotBytes = 2 * BM * 128;  // one ring slot: a [128 rows x 64 bf16] box for each column half of the tile
 constexpr int kStagePitch = 64;              // bytes per staged row: 32 bf16; 16 B chunks XOR-swizzled by (row >> 1) & 3
 constexpr int kBiasSlab = 512;               // bytes: the bias of the (up to) 128 columns one epilogue warp owns
-constexpr int kEpiStageBytes = 32 * kStagePitch + kBiasSlab;  // per epilogue warp: staging rows, then the bias slab
+constexpr int kEpiStageBytes = kBiasSlab + 32 * kStagePitch;  // per epilogue warp: the bias slab, then the staging rows (none in the fast kernels)
 constexpr int kSmemLimit = 227 * 1024;
 
 struct Params {
@@ -50,17 +51,21 @@ static unsigned g_mn_lbo = BK * 128, g_mn_sbo = 1024;
 static int g_dbg = 0;
 static long long g_fast_fallbacks = 0;   // fast-path launches that had no exact-stage kernel (see tvt_gemm)
 
-template <int BN, int kPlanes>
+template <int BN, int kPlanes, bool kSide, bool kFastEpi>
 struct Cfg {
   static constexpr int kAPlane = BM * BK * 2;
   static constexpr int kBPlane = BN * BK * 2;
   static constexpr int kStageBytes = kPlanes * (kAPlane + kBPlane);
-  static constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes;
-  static constexpr int kStages = (kSmemLimit - 2048 - kEpiBytes) / kStageBytes;
+  static constexpr int kEpiWarpBytes = kFastEpi ? kBiasSlab : kEpiStageBytes;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
+  static constexpr int kSideSlots = BN / 128;  // one per two 32-column chunk steps of the epilogue warps
+  static constexpr int kSideBytes = kSide ? kSideSlots * kSideSlotBytes : 0;
+  static constexpr int kStages = (kSmemLimit - 2048 - kEpiBytes - kSideBytes) / kStageBytes;
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * BN;  // 512 or 256: powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSideBytes + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(kStages >= 2, "need at least a double buffer");
+  static_assert(!kSide || kPlanes == 2 || kStages >= 3, "side-ring kernels keep three operand stages");
   static_assert(kSmemBytes <= kSmemLimit, "smem budget");
 };
 
@@ -91,20 +96,22 @@ __device__ __forceinline__ void store8(void* base, int is_f32, long long off, co
 //
 // kEpi selects how much of this is compiled in.  The loop around it is instruction-cache bound when everything
 // is present (an 80 KB kernel against a 32 KB L1.5 I$), so the hot combinations get their own small kernels:
-//   kEpiFast   : alpha, bias, relu, bf16 relu mask, dropout, bf16 residual -> staged bf16 output
+//   kEpiFast+st: alpha, bias and the stages in st (relu, bf16 relu mask, dropout, bf16 residual) -> bf16 output
 //   kEpiAtomic : split-K fp32 red.add only
 //   kEpiGeneric: every stage (fp32 operands, pre-activation store, gelu, hi/lo planes, fp32 output ...)
-// kEpiFast + a stage mask (kStRelu ...) compiles exactly those stages in, unconditionally; plain kEpiFast checks
-// every stage at run time (the fallback for combinations that have no instantiation).
-enum { kEpiGeneric = 0, kEpiFast = 1, kEpiAtomic = 2, kEpiFastExact = 16 };
+// kEpiFast + a stage mask (kStRelu ...) is a kernel with exactly those stages compiled in, unconditionally.
+enum { kEpiGeneric = 0, kEpiAtomic = 2, kEpiFast = 16 };
 enum { kStRelu = 1, kStMask = 2, kStDrop = 4, kStRes = 8 };
-__host__ __device__ constexpr bool is_fast(int kEpi) { return kEpi == kEpiFast || kEpi >= kEpiFastExact; }
-// does a fast kernel run stage st?  (compile-time constant for the exact kernels)
-template <int kEpi>
-__device__ __forceinline__ bool has_stage(int st, bool runtime) {
-  if constexpr (kEpi >= kEpiFastExact) return ((kEpi - kEpiFastExact) & st) != 0;
-  else return runtime;
-}
+__host__ __device__ constexpr bool is_fast(int kEpi) { return kEpi >= kEpiFast; }
+__host__ __device__ constexpr bool has_stage(int kEpi, int st) { return kEpi >= kEpiFast && ((kEpi - kEpiFast) & st) != 0; }
+// Fast kernels with a bf16 side operand (relu mask or residual) fetch it one of two ways:
+//   ring (default): TMA streams it through a shared-memory ring about one tile-epilogue ahead of its use.  The
+//     ring costs one of the four operand stages, which a short-K (epilogue-bound) problem does not miss;
+//   kSideLdg: each lane loads its row's 64 B one chunk ahead with 256-bit loads.  Slow per byte, but free of shared
+//     memory: for long-K problems, where the epilogue has slack and the main loop wants all four stages.
+enum { kSideLdg = 32 };
+__host__ __device__ constexpr bool side_ldg(int kEpi) { return kEpi >= kEpiFast && ((kEpi - kEpiFast) & kSideLdg) != 0 && has_stage(kEpi, kStMask | kStRes); }
+__host__ __device__ constexpr bool has_side(int kEpi) { return has_stage(kEpi, kStMask | kStRes) && !side_ldg(kEpi); }
 
 __device__ __forceinline__ void epilogue_atomic(const Params& p, long long row, int col0, int ng, const float (&v)[32]) {
   float* dst = p.out_f32 + row * p.ld_f32 + col0;
@@ -253,18 +260,18 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, float scale, uint
     v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), scale, __uint_as_float(b.z));
     v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), scale, __uint_as_float(b.w));
   }
-  if (has_stage<kEpi>(kStRelu, p.act == TVT_ACT_RELU)) {
+  if constexpr (has_stage(kEpi, kStRelu)) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
   }
-  if (has_stage<kEpi>(kStMask, p.relu_mask != nullptr)) {   // keep where the bf16 mask value is > 0: integer tests on the packed halves
+  if constexpr (has_stage(kEpi, kStMask)) {   // keep where the bf16 mask value is > 0: integer tests on the packed halves
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       v[2 * i] = static_cast<int>(side[i] << 16) > 0 ? v[2 * i] : 0.0f;
       v[2 * i + 1] = static_cast<int>(side[i]) >= 0x10000 ? v[2 * i + 1] : 0.0f;
     }
   }
-  if (has_stage<kEpi>(kStDrop, p.dropout_thr16 != 0)) {
+  if constexpr (has_stage(kEpi, kStDrop)) {
     const uint32_t thr_hi = p.dropout_thr16 << 16;   // (w >> 16) >= thr  <=>  w >= thr << 16
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -276,7 +283,7 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, float scale, uint
       v[4 * q + 3] = hi >= thr_hi ? v[4 * q + 3] : 0.0f;
     }
   }
-  if (has_stage<kEpi>(kStRes, p.residual != nullptr)) {
+  if constexpr (has_stage(kEpi, kStRes)) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       v[2 * i] += __uint_as_float(side[i] << 16);
@@ -332,18 +339,22 @@ template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-            const Params p) {
-  using C = Cfg<BN, kPlanes>;
+            const __grid_constant__ CUtensorMap tmSide, const Params p) {
+  constexpr bool kSide = has_side(kEpi);
+  using C = Cfg<BN, kPlanes, kSide, is_fast(kEpi)>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* epi_stage = smem + C::kStages * C::kStageBytes;
+  uint8_t* side_ring = smem + C::kStages * C::kStageBytes;   // 1024-aligned: SWIZZLE_64B boxes need 512
+  uint8_t* epi_stage = side_ring + C::kSideBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + C::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::kStages;
   uint64_t* tfull_bar = bars + 2 * C::kStages;
   uint64_t* tempty_bar = tfull_bar + C::kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + C::kAccStages);
+  uint64_t* sfull_bar = tempty_bar + C::kAccStages;          // side ring: slot filled by TMA
+  uint64_t* sempty_bar = sfull_bar + C::kSideSlots;          // slot read by all epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty_bar + C::kSideSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -356,6 +367,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int s = 0; s < C::kAccStages; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
       mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);  // one arrive per epilogue warp
+    }
+    for (int s = 0; s < C::kSideSlots; ++s) {
+      mbar_init(smem_u32(&sfull_bar[s]), 1);
+      mbar_init(smem_u32(&sempty_bar[s]), kEpiWarps);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -461,40 +476,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++as == C::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
-  } else {
+  } else if (warp == kEpiWarps + 2) {
+    if constexpr (kSide) {
+      if (lane == 0) {
+        // slot c of the ring holds, for chunk steps 2c and 2c+1 of the epilogue, the [128 x 64] block each column
+        // half's warps read; it is refilled for this CTA's next tile as soon as all eight warps have copied it to registers, so the
+        // side operand runs about one tile-epilogue ahead of its use.  Out-of-range rows / columns arrive as zeros.
+        tma_prefetch_desc(&tmSide);
+        uint32_t sphase = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+          const int n_blk = w % num_n;
+          const int m_blk = (w / num_n) % num_m;
+#pragma unroll 1
+          for (int c = 0; c < C::kSideSlots; ++c) {
+            if (p.dbg & 16) break;
+            mbar_wait(smem_u32(&sempty_bar[c]), sphase ^ 1);
+            const uint32_t fb = smem_u32(&sfull_bar[c]);
+            mbar_arrive_expect_tx(fb, kSideSlotBytes);
+            const uint32_t dst = smem_u32(side_ring + c * kSideSlotBytes);
+            tma_load_2d(dst, &tmSide, fb, n_blk * BN + c * 64, m_blk * BM);
+            tma_load_2d(dst + kSideSlotBytes / 2, &tmSide, fb, n_blk * BN + BN / 2 + c * 64, m_blk * BM);
+          }
+          sphase ^= 1;
+        }
+      }
+    }
+  } else if (warp < kEpiWarps) {
     const int ew = warp;
     const int quad = ew & 3;     // == warp % 4: the TMEM lane quadrant this warp may read
     const int half = ew >> 2;    // which half of the tile's columns this warp drains
-    const uint32_t stage_addr = smem_u32(epi_stage + ew * kEpiStageBytes);
+    const uint32_t bias_addr = smem_u32(epi_stage + ew * C::kEpiWarpBytes);   // this warp's bias slab
+    const uint32_t stage_addr = bias_addr + kBiasSlab;                       // and its staging rows
     const bool staged = kEpi == kEpiGeneric && p.out_bf16 != nullptr && p.out_bf16_lo == nullptr && !p.atomic_out;
     int as = 0;
     uint32_t aphase = 0;
-    // kEpiFast state that lives across tiles (dead code in the other kernels)
-    const __nv_bfloat16* side_base = reinterpret_cast<const __nv_bfloat16*>(p.residual ? p.residual : p.relu_mask);
-    const bool has_side = has_stage<kEpi>(kStMask | kStRes, side_base != nullptr);
-    const long long ld_side = p.residual ? p.ld_residual : p.ld_mask;
-    const float dscale = has_stage<kEpi>(kStDrop, p.dropout_thr16 != 0) ? p.dropout_scale : 1.0f;
+    // fast-kernel state that lives across tiles (dead code in the other kernels)
+    const float dscale = has_stage(kEpi, kStDrop) ? p.dropout_scale : 1.0f;
     const float scale = p.alpha * dscale;
-    uint32_t side_a[16], side_b[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) side_a[i] = side_b[i] = 0;
-    bool a_valid = false, bias_valid = false;
+    bool bias_valid = false;
     float4 bias_nx = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t sphase = 0;
     auto load_bias = [&](int cb) {
       const int c = cb + 4 * lane;
       return (p.bias && c < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    // L2-prefetch this warp's [32 x BN/2] slab of a tile's mask / residual (128 B lines)
-    auto prefetch_slab = [&](int wt) {
-      const long long prow0 = static_cast<long long>((wt / num_n) % num_m) * BM + quad * 32;
-      const int pcol = (wt % num_n) * BN + half * (BN / 2);
-#pragma unroll
-      for (int j = 0; j < BN / 128; ++j) {
-        const int line = lane + 32 * j;
-        const long long pr = prow0 + line / (BN / 128);
-        const int pc = pcol + (line % (BN / 128)) * 64;
-        if (pr < p.M && pc < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(side_base + pr * ld_side + pc));
-      }
     };
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int n_blk = w % num_n;
@@ -509,60 +533,69 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // one chunk ahead: the first fetch is issued before waiting for the accumulator, the next one while the
       // current chunk is processed
       if constexpr (is_fast(kEpi)) {
-        // thread == row throughout.  The row's mask / residual values arrive by 256-bit loads issued one chunk
-        // ahead into the other of two register buffers (across tile boundaries too; an L2 prefetch of the whole
-        // slab runs one tile ahead), the bf16 result leaves by 256-bit stores.
+        // thread == row throughout: the row's 32 mask / residual values of a chunk come from the TMA-fed ring, the
+        // bf16 result leaves by 256-bit stores.  The bias of the next tile is fetched a tile ahead.
         const int colbase = n_blk * BN + half * (BN / 2);
-        const __nv_bfloat16* side_row = side_base + row * ld_side;
-        const bool ld_ok = has_side && row < p.M && !(p.dbg & 16);
         const int wn = w + static_cast<int>(gridDim.x);
         const bool has_next = wn < total;
-        const long long row_n = static_cast<long long>((wn / num_n) % num_m) * BM + quad * 32 + lane;
-        const int colbase_n = (wn % num_n) * BN + half * (BN / 2);
-        if (has_side && !(p.dbg & 32)) {
-          if (w == static_cast<int>(blockIdx.x)) prefetch_slab(w);
-          if (has_next) prefetch_slab(wn);
-        }
-        if (!a_valid && ld_ok && colbase < p.N) { ldg256(side_row + colbase, side_a); ldg256(side_row + colbase + 16, side_a + 8); }
         if (4 * lane < BN / 2) {   // this warp's bias columns (pre-scaled; zeros without a bias) -> shared memory
           if (!bias_valid) bias_nx = load_bias(colbase);
-          sts128(stage_addr + 32 * kStagePitch + 16 * lane, __float_as_uint(bias_nx.x * dscale), __float_as_uint(bias_nx.y * dscale),
+          sts128(bias_addr + 16 * lane, __float_as_uint(bias_nx.x * dscale), __float_as_uint(bias_nx.y * dscale),
                  __float_as_uint(bias_nx.z * dscale), __float_as_uint(bias_nx.w * dscale));
-          if (has_next) bias_nx = load_bias(colbase_n);
+          if (has_next) bias_nx = load_bias((wn % num_n) * BN + half * (BN / 2));
         }
         bias_valid = has_next;
         __syncwarp();
+        uint32_t side[16];
+        const __nv_bfloat16* side_row = nullptr;
+        if constexpr (side_ldg(kEpi)) {   // first chunk's mask / residual values, in flight while the main loop finishes
+          side_row = reinterpret_cast<const __nv_bfloat16*>(has_stage(kEpi, kStRes) ? p.residual : p.relu_mask) +
+                     row * (has_stage(kEpi, kStRes) ? p.ld_residual : p.ld_mask);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) side[i] = 0;
+          if (row < p.M && colbase < p.N) { ldg256(side_row + colbase, side); ldg256(side_row + colbase + 16, side + 8); }
+        }
         mbar_wait(smem_u32(&tfull_bar[as]), aphase);
         tc_fence_after();
-        // one chunk: start the TMEM load, start the side loads of the chunk after it, then finish this one
-        auto chunk = [&](int c, const uint32_t (&cur)[16], uint32_t (&nxt)[16], const __nv_bfloat16* nxt_ptr, bool nxt_ok) {
+        const int trow = quad * 32 + lane;   // row inside the tile
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
           const int tcol = half * (BN / 2) + c * 32;   // column inside the tile
           const int col0 = n_blk * BN + tcol;
           const bool live = col0 < p.N && !(p.dbg & 8);   // warp-uniform
           uint32_t r[32];
           if (live) tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + tcol, r);
-          if (nxt_ok) { ldg256(nxt_ptr, nxt); ldg256(nxt_ptr + 16, nxt + 8); }
-          if (!live) return;
+          if constexpr (kSide) {   // copy this row's 64 B out of the slot (SWIZZLE_128B: 16 B chunk ^ (row & 7)); free it after its second half
+            const int slot = c >> 1;
+            if ((c & 1) == 0 && !(p.dbg & 16)) mbar_wait(smem_u32(&sfull_bar[slot]), sphase);
+            const uint32_t srow = smem_u32(side_ring + slot * kSideSlotBytes) + half * (kSideSlotBytes / 2) + trow * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 q = lds128(srow + ((((c & 1) * 4 + g) ^ (trow & 7)) << 4));
+              side[4 * g] = q.x; side[4 * g + 1] = q.y; side[4 * g + 2] = q.z; side[4 * g + 3] = q.w;
+            }
+            if (c & 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&sempty_bar[slot]));
+            }
+          }
+          if (!live) continue;
           tmem_ld_wait_dep(r);
-          if ((p.dbg & 3) == 1) return;
+          if ((p.dbg & 3) == 1) continue;
           const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;   // multiple of 8: + q never carries
           uint32_t out[16];
-          epilogue_fast<kEpi>(p, scale, stage_addr + 32 * kStagePitch + c * 128, static_cast<uint32_t>(e4),
-                        static_cast<uint32_t>(e4 >> 32) ^ static_cast<uint32_t>(p.dropout_seed >> 32), r, cur, out);
+          epilogue_fast<kEpi>(p, scale, bias_addr + c * 128, static_cast<uint32_t>(e4),
+                              static_cast<uint32_t>(e4 >> 32) ^ static_cast<uint32_t>(p.dropout_seed >> 32), r, side, out);
+          if constexpr (side_ldg(kEpi)) {
+            if (c + 1 < BN / 64 && col0 + 32 < p.N && row < p.M) { ldg256(side_row + col0 + 32, side); ldg256(side_row + col0 + 48, side + 8); }
+          }
           if (row_ok && (p.dbg & 3) != 2) {
             __nv_bfloat16* orow = p.out_bf16 + row * p.ld_bf16 + col0;
             stg256(orow, out);
             stg256(orow + 16, out + 8);
           }
-        };
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; c += 2) {
-          chunk(c, side_a, side_b, side_row + colbase + 32 * (c + 1), ld_ok && colbase + 32 * (c + 1) < p.N);
-          const bool last = c + 2 >= BN / 64;   // then the other buffer receives chunk 0 of this CTA's next tile
-          chunk(c + 1, side_b, side_a, last ? side_base + row_n * ld_side + colbase_n : side_row + colbase + 32 * (c + 2),
-                last ? (has_next && has_side && row_n < p.M && colbase_n < p.N && !(p.dbg & 16)) : (ld_ok && colbase + 32 * (c + 2) < p.N));
         }
-        a_valid = has_next;
+        sphase ^= 1;
         __syncwarp();   // every lane is done with the bias slab before the next tile overwrites it
       } else {
         const bool pre = kEpi == kEpiGeneric && !p.atomic_out;
@@ -591,7 +624,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (4 * lane < BN / 2) {
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
               if (c < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-              sts128(stage_addr + 32 * kStagePitch + 16 * lane, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+              sts128(bias_addr + 16 * lane, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
             }
             __syncwarp();
           }
@@ -625,7 +658,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           const int ng = (p.N - col0) >= 32 ? 4 : (p.N - col0) >> 3;
-          if (row_ok) epilogue32<kEpi>(p, row, col0, ng, v, mask_pk, res_pk, pre, stage_addr + 32 * kStagePitch + c * 128);
+          if (row_ok) epilogue32<kEpi>(p, row, col0, ng, v, mask_pk, res_pk, pre, bias_addr + c * 128);
           if (staged) {
             // thread == row: four 16 B chunks, XOR-swizzled so neither this write nor the read-back below conflicts
             const uint32_t wbase = stage_addr + lane * kStagePitch;
@@ -683,7 +716,7 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D bf16 tensor map with 128B swizzle: dims {inner, outer}, row pitch ld elements.
 static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long outer, long long ld,
-                    int box_inner, int box_outer) {
+                    int box_inner, int box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -694,7 +727,7 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld)",
@@ -706,8 +739,8 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
 
 template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi>
 static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) {
-  using C = Cfg<BN, kPlanes>;
-  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  using C = Cfg<BN, kPlanes, has_side(kEpi), is_fast(kEpi)>;
+  CUtensorMap tmA, tmAlo, tmB, tmBlo, tmSide;
   int rc;
   auto mapA = [&](CUtensorMap* m, const void* ptr) {
     return kAMN ? make_map(m, ptr, a->m, a->k, a->lda, 64, BK) : make_map(m, ptr, a->k, a->m, a->lda, BK, BM);
@@ -724,6 +757,11 @@ static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) 
     tmAlo = tmA;
     tmBlo = tmB;
   }
+  tmSide = tmA;
+  if constexpr (has_side(kEpi)) {   // the row-major [m, n] bf16 mask / residual, in [128 x 64] boxes
+    const bool res = has_stage(kEpi, kStRes);
+    if ((rc = make_map(&tmSide, res ? a->residual : a->relu_mask, a->n, a->m, res ? a->ld_residual : a->ld_mask, 64, BM)) != TVT_OK) return rc;
+  }
   auto kern = gemm_kernel<BN, kAMN, kBMN, kPlanes, kEpi>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -737,7 +775,7 @@ static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) 
   const long long num_m = (a->m + BM - 1) / BM, num_n = (a->n + BN - 1) / BN;
   const long long total = num_m * num_n * p.splits;
   const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, p);
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, tmSide, p);
   return check_launch("tvt_gemm");
 }
 
@@ -837,13 +875,13 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   const long long c256 = ((w256 + nsm - 1) / nsm) * (kb_per * 512 + 3000);
   const long long c128 = ((w128 + nsm - 1) / nsm) * (kb_per * 400 + 1800);
   const bool narrow = a->n <= 128 || c128 < c256;
-  // Epilogue kind: the small specialised kernels whenever the request fits them (see epilogue32); the fast one
-  // moves whole 32 B sectors per lane, so its row-major bf16 operands must be 32-byte aligned row by row
+  // Epilogue kind: the small specialised kernels whenever the request fits them (see epilogue32); the fast ones
+  // store whole 32 B sectors per lane, so the bf16 output must be 32-byte aligned row by row
   auto al32 = [](const void* ptr, long long ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0); };
   const bool fast = !a->atomic_out && a->out_bf16 && !a->out_bf16_lo && !a->out_f32 && !a->out_preact && !a->gelu_gate &&
                     (a->act == TVT_ACT_NONE || a->act == TVT_ACT_RELU) && !(a->residual && a->residual_dtype == TVT_F32) &&
                     !(a->relu_mask && a->mask_dtype == TVT_F32) && !(a->residual && a->relu_mask) && a->n % 32 == 0 &&
-                    al32(a->out_bf16, a->ld_bf16) && al32(a->residual, a->ld_residual) && al32(a->relu_mask, a->ld_mask);
+                    al32(a->out_bf16, a->ld_bf16);
   if (a->a_lo) {
     if (a->atomic_out) return gemm::dispatch_width<2, gemm::kEpiAtomic>(narrow, a, p, s);
     return gemm::dispatch_width<2, gemm::kEpiGeneric>(narrow, a, p, s);
@@ -854,9 +892,15 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     // B MN-major); anything else takes the fast kernel that checks its stages at run time
     using namespace gemm;
     const int st = (a->act == TVT_ACT_RELU ? kStRelu : 0) | (a->relu_mask ? kStMask : 0) | (a->dropout_p > 0.0f ? kStDrop : 0) | (a->residual ? kStRes : 0);
+    const bool side_al32 = al32(a->residual, a->ld_residual) && al32(a->relu_mask, a->ld_mask);
+    const bool ldg = (st & (kStMask | kStRes)) && kb_per > 16 && side_al32;   // long K: keep four operand stages (see kSideLdg)
 #define TVT_FAST_CASE(AMN, BMN, ST)                                                                                   \
-  if (a->a_mn_major == AMN && a->b_mn_major == BMN && st == (ST))                                                     \
-    return narrow ? launch<128, AMN, BMN, 1, kEpiFastExact + (ST)>(a, p, s) : launch<256, AMN, BMN, 1, kEpiFastExact + (ST)>(a, p, s);
+  if (a->a_mn_major == AMN && a->b_mn_major == BMN && st == (ST)) {                                                   \
+    if (((ST) & (kStMask | kStRes)) && ldg)                                                                           \
+      return narrow ? launch<128, AMN, BMN, 1, kEpiFast + kSideLdg + (ST)>(a, p, s)                                   \
+                    : launch<256, AMN, BMN, 1, kEpiFast + kSideLdg + (ST)>(a, p, s);                                  \
+    return narrow ? launch<128, AMN, BMN, 1, kEpiFast + (ST)>(a, p, s) : launch<256, AMN, BMN, 1, kEpiFast + (ST)>(a, p, s); \
+  }
     TVT_FAST_CASE(false, false, 0)
     TVT_FAST_CASE(false, false, kStRelu)
     TVT_FAST_CASE(false, false, kStRelu | kStDrop)
@@ -869,8 +913,7 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     TVT_FAST_CASE(false, true, kStMask | kStDrop)
     TVT_FAST_CASE(false, true, kStDrop)
 #undef TVT_FAST_CASE
-    ++g_fast_fallbacks;
-    return dispatch_width<1, kEpiFast>(narrow, a, p, s);
+    ++g_fast_fallbacks;   // no exact kernel for this combination: the generic one below
   }
   return gemm::dispatch_width<1, gemm::kEpiGeneric>(narrow, a, p, s);
 }
