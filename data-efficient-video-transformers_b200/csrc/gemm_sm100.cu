@@ -11,6 +11,7 @@
 // Work item = (split, m_block, n_block); split-K partials are combined with red.global.add.f32.
 // Operand storage is selected per operand (K-major or MN-major) through the UMMA descriptors, so the
 // forward (X W^T), dgrad (dY W) and wgrad (dY^T X) products all read the tensors as torch stores them.
+#include <cstdlib>
 #include <cuda.h>
 #include <mutex>
 
@@ -49,12 +50,14 @@ struct Params {
 
 static unsigned g_mn_lbo = BK * 128, g_mn_sbo = 1024;
 static int g_dbg = 0;
+static int g_pair = [] { const char* e = getenv("TVT_GEMM_PAIR"); return e ? atoi(e) : 1; }();   // bring-up knob: 0 = never use the CTA-pair kernels
 static long long g_fast_fallbacks = 0;   // fast-path launches that had no exact-stage kernel (see tvt_gemm)
 
-template <int BN, int kPlanes, bool kSide, bool kFastEpi>
+template <int BN, int kPlanes, bool kSide, bool kFastEpi, bool kCta2 = false>
 struct Cfg {
   static constexpr int kAPlane = BM * BK * 2;
-  static constexpr int kBPlane = BN * BK * 2;
+  static constexpr int kBRows = kCta2 ? BN / 2 : BN;   // a CTA pair splits the B tile between its two CTAs
+  static constexpr int kBPlane = kBRows * BK * 2;
   static constexpr int kStageBytes = kPlanes * (kAPlane + kBPlane);
   static constexpr int kEpiWarpBytes = kFastEpi ? kBiasSlab : kEpiStageBytes;
   static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
@@ -335,13 +338,20 @@ __device__ __forceinline__ void fetch_land(const uint4 (&t)[4], uint32_t stage_a
   __syncwarp();
 }
 
-template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi>
+// kCta2: the CTA pair of a 2-cluster computes one [256 x BN] tile with cta_group::2 MMAs issued by the leader (rank
+// 0).  Each CTA loads its own 128 rows of A and BN/2 rows of B (a third less shared-memory fill and L2 traffic per
+// flop, so more stages fit), accumulates its 128 rows in its own TMEM and runs its own epilogue.  Cross-CTA
+// signalling: both CTAs' TMA loads count on the leader's full barrier; the leader's commits multicast to both
+// CTAs' empty / accumulator-full barriers; the peer's epilogue warps arrive remotely on the leader's
+// accumulator-empty barrier.
+template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi, bool kCta2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
             const __grid_constant__ CUtensorMap tmSide, const Params p) {
   constexpr bool kSide = has_side(kEpi);
-  using C = Cfg<BN, kPlanes, kSide, is_fast(kEpi)>;
+  using C = Cfg<BN, kPlanes, kSide, is_fast(kEpi), kCta2>;
+  constexpr int kCtas = kCta2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -358,6 +368,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCta2 ? cluster_ctarank() : 0;
+  const int w0 = kCta2 ? blockIdx.x >> 1 : blockIdx.x;        // first tile and tile stride of this CTA (pair)
+  const int wstep = kCta2 ? gridDim.x >> 1 : gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -366,7 +379,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < C::kAccStages; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps * kCtas);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int s = 0; s < C::kSideSlots; ++s) {
       mbar_init(smem_u32(&sfull_bar[s]), 1);
@@ -377,15 +390,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
   }
   if (warp == kEpiWarps + 1) {
-    tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (kCta2) {
+      tmem_alloc_cta2(smem_u32(tmem_slot), C::kTmemCols);
+      tmem_relinquish_cta2();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_m = (p.M + BM - 1) / BM;
+  const int num_m = (p.M + BM * kCtas - 1) / (BM * kCtas);
   const int num_n = (p.N + BN - 1) / BN;
   const int total = num_m * num_n * p.splits;
   const int kb_total = (p.K + BK - 1) / BK;
@@ -394,18 +412,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int w = w0; w < total; w += wstep) {
         const int n_blk = w % num_n;
         const int t = w / num_n;
-        const int m_blk = t % num_m;
+        const int m_row = ((t % num_m) * kCtas + cta_rank) * BM;            // first A row of this CTA
+        const int n_row = n_blk * BN + cta_rank * C::kBRows;                // first B row of this CTA
         const int split = t / num_m;
         const int kb0 = static_cast<int>(static_cast<long long>(split) * kb_total / p.splits);
         const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           if (p.dbg & 4) break;
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, C::kStageBytes);
+          // pair: the leader's barrier counts the bytes of both CTAs' loads
+          const uint32_t fb = kCta2 ? mapa_u32(smem_u32(&full_bar[stage]), 0) : smem_u32(&full_bar[stage]);
+          if (cta_rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), C::kStageBytes * kCtas);
+          auto tma = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+            if constexpr (kCta2) tma_load_2d_cta2(dst, m, fb, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
+          };
           uint8_t* st = smem + stage * C::kStageBytes;
 #pragma unroll
           for (int pl = 0; pl < kPlanes; ++pl) {
@@ -414,18 +437,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t sa = smem_u32(st + pl * C::kAPlane);
             const uint32_t sb = smem_u32(st + kPlanes * C::kAPlane + pl * C::kBPlane);
             if constexpr (!kAMN) {
-              tma_load_2d(sa, ma, fb, kb * BK, m_blk * BM);
+              tma(sa, ma, kb * BK, m_row);
             } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j)
-                tma_load_2d(sa + j * (BK * 128), ma, fb, m_blk * BM + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma(sa + j * (BK * 128), ma, m_row + j * 64, kb * BK);
             }
             if constexpr (!kBMN) {
-              tma_load_2d(sb, mb, fb, kb * BK, n_blk * BN);
+              tma(sb, mb, kb * BK, n_row);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(sb + j * (BK * 128), mb, fb, n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < C::kBRows / 64; ++j) tma(sb + j * (BK * 128), mb, n_row + j * 64, kb * BK);
             }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -433,13 +454,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, kAMN, kBMN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * kCtas, BN, kAMN, kBMN);
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (kCta2) tc_commit_cta2(smem_u32(bar), 3); else tc_commit(smem_u32(bar));
+      };
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int w = w0; w < total; w += wstep) {
         const int split = (w / num_n) / num_m;
         const int kb0 = static_cast<int>(static_cast<long long>(split) * kb_total / p.splits);
         const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
@@ -465,14 +489,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                           : make_smem_desc_sw128(sa + k * 32, 16, 1024);
               const uint64_t bdesc = kBMN ? make_smem_desc_sw128(sb + k * 16 * 128, p.mn_lbo, p.mn_sbo)
                                           : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-              tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+              if constexpr (kCta2) tc_mma_f16_ss_cta2(d_tmem, adesc, bdesc, idesc, accumulate);
+              else tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
               accumulate = 1;
             }
           }
-          tc_commit(smem_u32(&empty_bar[stage]));
+          commit(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(smem_u32(&tfull_bar[as]));
+        commit(&tfull_bar[as]);
         if (++as == C::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
@@ -484,9 +509,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // side operand runs about one tile-epilogue ahead of its use.  Out-of-range rows / columns arrive as zeros.
         tma_prefetch_desc(&tmSide);
         uint32_t sphase = 0;
-        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int w = w0; w < total; w += wstep) {
           const int n_blk = w % num_n;
-          const int m_blk = (w / num_n) % num_m;
+          const int m_row = (((w / num_n) % num_m) * kCtas + cta_rank) * BM;
 #pragma unroll 1
           for (int c = 0; c < C::kSideSlots; ++c) {
             if (p.dbg & 16) break;
@@ -494,8 +519,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t fb = smem_u32(&sfull_bar[c]);
             mbar_arrive_expect_tx(fb, kSideSlotBytes);
             const uint32_t dst = smem_u32(side_ring + c * kSideSlotBytes);
-            tma_load_2d(dst, &tmSide, fb, n_blk * BN + c * 64, m_blk * BM);
-            tma_load_2d(dst + kSideSlotBytes / 2, &tmSide, fb, n_blk * BN + BN / 2 + c * 64, m_blk * BM);
+            tma_load_2d(dst, &tmSide, fb, n_blk * BN + c * 64, m_row);
+            tma_load_2d(dst + kSideSlotBytes / 2, &tmSide, fb, n_blk * BN + BN / 2 + c * 64, m_row);
           }
           sphase ^= 1;
         }
@@ -520,13 +545,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int c = cb + 4 * lane;
       return (p.bias && c < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    for (int w = w0; w < total; w += wstep) {
       const int n_blk = w % num_n;
       const int m_blk = (w / num_n) % num_m;
       const int split = (w / num_n) / num_m;
       const int kb0 = static_cast<int>(static_cast<long long>(split) * kb_total / p.splits);
       const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * kb_total / p.splits);
-      const long long row0 = static_cast<long long>(m_blk) * BM + quad * 32;
+      const long long row0 = (static_cast<long long>(m_blk) * kCtas + cta_rank) * BM + quad * 32;
       const long long row = row0 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       // operands of the fused stages that live in global memory are fetched coalesced (one warp = 32 rows) and
@@ -536,7 +561,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // thread == row throughout: the row's 32 mask / residual values of a chunk come from the TMA-fed ring, the
         // bf16 result leaves by 256-bit stores.  The bias of the next tile is fetched a tile ahead.
         const int colbase = n_blk * BN + half * (BN / 2);
-        const int wn = w + static_cast<int>(gridDim.x);
+        const int wn = w + wstep;
         const bool has_next = wn < total;
         if (4 * lane < BN / 2) {   // this warp's bias columns (pre-scaled; zeros without a bias) -> shared memory
           if (!bias_valid) bias_nx = load_bias(colbase);
@@ -684,15 +709,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+      if (lane == 0) {
+        if constexpr (kCta2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA warp waits on it
+        else mbar_arrive(smem_u32(&tempty_bar[as]));
+      }
       if (++as == C::kAccStages) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCta2) cluster_sync_all(); else __syncthreads();   // pair: neither CTA may exit while the other can still reach it
   tc_fence_after();
-  if (warp == kEpiWarps + 1) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == kEpiWarps + 1) {
+    if constexpr (kCta2) tmem_dealloc_cta2(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -737,16 +767,16 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
   return TVT_OK;
 }
 
-template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi>
+template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi, bool kCta2 = false>
 static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) {
-  using C = Cfg<BN, kPlanes, has_side(kEpi), is_fast(kEpi)>;
+  using C = Cfg<BN, kPlanes, has_side(kEpi), is_fast(kEpi), kCta2>;
   CUtensorMap tmA, tmAlo, tmB, tmBlo, tmSide;
   int rc;
   auto mapA = [&](CUtensorMap* m, const void* ptr) {
     return kAMN ? make_map(m, ptr, a->m, a->k, a->lda, 64, BK) : make_map(m, ptr, a->k, a->m, a->lda, BK, BM);
   };
   auto mapB = [&](CUtensorMap* m, const void* ptr) {
-    return kBMN ? make_map(m, ptr, a->n, a->k, a->ldb, 64, BK) : make_map(m, ptr, a->k, a->n, a->ldb, BK, BN);
+    return kBMN ? make_map(m, ptr, a->n, a->k, a->ldb, 64, BK) : make_map(m, ptr, a->k, a->n, a->ldb, BK, C::kBRows);
   };
   if ((rc = mapA(&tmA, a->a)) != TVT_OK) return rc;
   if ((rc = mapB(&tmB, a->b)) != TVT_OK) return rc;
@@ -762,7 +792,7 @@ static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) 
     const bool res = has_stage(kEpi, kStRes);
     if ((rc = make_map(&tmSide, res ? a->residual : a->relu_mask, a->n, a->m, res ? a->ld_residual : a->ld_mask, 64, BM)) != TVT_OK) return rc;
   }
-  auto kern = gemm_kernel<BN, kAMN, kBMN, kPlanes, kEpi>;
+  auto kern = gemm_kernel<BN, kAMN, kBMN, kPlanes, kEpi, kCta2>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -772,10 +802,32 @@ static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) 
     set_last_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(attr_err));
     return TVT_ECUDA;
   }
-  const long long num_m = (a->m + BM - 1) / BM, num_n = (a->n + BN - 1) / BN;
-  const long long total = num_m * num_n * p.splits;
-  const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, tmSide, p);
+  constexpr int kCtas = kCta2 ? 2 : 1;
+  const long long num_m = (a->m + BM * kCtas - 1) / (BM * kCtas), num_n = (a->n + BN - 1) / BN;
+  const long long total = num_m * num_n * p.splits;   // tiles (of a CTA pair when kCta2)
+  const long long slots = num_sms() / kCtas;
+  const int grid = static_cast<int>(total < slots ? total : slots) * kCtas;
+  if constexpr (kCta2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmAlo, tmB, tmBlo, tmSide, p);
+    if (e != cudaSuccess) {
+      set_last_error("tvt_gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      return TVT_ECUDA;
+    }
+  } else {
+    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, tmSide, p);
+  }
   return check_launch("tvt_gemm");
 }
 
@@ -802,6 +854,7 @@ extern "C" void tvt_debug_set_mn_desc(unsigned lbo, unsigned sbo) {
 }
 
 extern "C" void tvt_debug_set_epilogue(int mode) { tvt::gemm::g_dbg = mode; }
+extern "C" void tvt_debug_set_pair(int on) { tvt::gemm::g_pair = on; }
 extern "C" long long tvt_debug_gemm_fast_fallbacks() { return tvt::gemm::g_fast_fallbacks; }
 
 extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
@@ -886,7 +939,18 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     if (a->atomic_out) return gemm::dispatch_width<2, gemm::kEpiAtomic>(narrow, a, p, s);
     return gemm::dispatch_width<2, gemm::kEpiGeneric>(narrow, a, p, s);
   }
-  if (a->atomic_out) return gemm::dispatch_width<1, gemm::kEpiAtomic>(narrow, a, p, s);
+  // CTA pairs ([256 x 256] tiles) whenever 256-wide tiles are chosen and pairing does not add a wave
+  const long long wpair = ((a->m + 255) / 256) * ((a->n + 255) / 256) * a->splits, npair = nsm / 2;
+  const bool pair = !narrow && gemm::g_pair && (wpair + npair - 1) / npair <= (w256 + nsm - 1) / nsm;   // no extra wave
+  if (a->atomic_out) {
+    if (pair) {
+      if (!a->a_mn_major && !a->b_mn_major) return gemm::launch<256, false, false, 1, gemm::kEpiAtomic, true>(a, p, s);
+      if (!a->a_mn_major && a->b_mn_major) return gemm::launch<256, false, true, 1, gemm::kEpiAtomic, true>(a, p, s);
+      if (a->a_mn_major && a->b_mn_major) return gemm::launch<256, true, true, 1, gemm::kEpiAtomic, true>(a, p, s);
+      return gemm::launch<256, true, false, 1, gemm::kEpiAtomic, true>(a, p, s);
+    }
+    return gemm::dispatch_width<1, gemm::kEpiAtomic>(narrow, a, p, s);
+  }
   if (fast) {
     // exact-stage kernels for the combinations the encoder layers launch (forward: both operands K-major; dgrad:
     // B MN-major); anything else takes the fast kernel that checks its stages at run time
@@ -894,12 +958,13 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     const int st = (a->act == TVT_ACT_RELU ? kStRelu : 0) | (a->relu_mask ? kStMask : 0) | (a->dropout_p > 0.0f ? kStDrop : 0) | (a->residual ? kStRes : 0);
     const bool side_al32 = al32(a->residual, a->ld_residual) && al32(a->relu_mask, a->ld_mask);
     const bool ldg = (st & (kStMask | kStRes)) && kb_per > 16 && side_al32;   // long K: keep four operand stages (see kSideLdg)
+#define TVT_FAST_KIND(AMN, BMN, KIND)                                                                                 \
+  return narrow ? launch<128, AMN, BMN, 1, KIND>(a, p, s)                                                             \
+                : (pair ? launch<256, AMN, BMN, 1, KIND, true>(a, p, s) : launch<256, AMN, BMN, 1, KIND>(a, p, s));
 #define TVT_FAST_CASE(AMN, BMN, ST)                                                                                   \
   if (a->a_mn_major == AMN && a->b_mn_major == BMN && st == (ST)) {                                                   \
-    if (((ST) & (kStMask | kStRes)) && ldg)                                                                           \
-      return narrow ? launch<128, AMN, BMN, 1, kEpiFast + kSideLdg + (ST)>(a, p, s)                                   \
-                    : launch<256, AMN, BMN, 1, kEpiFast + kSideLdg + (ST)>(a, p, s);                                  \
-    return narrow ? launch<128, AMN, BMN, 1, kEpiFast + (ST)>(a, p, s) : launch<256, AMN, BMN, 1, kEpiFast + (ST)>(a, p, s); \
+    if (((ST) & (kStMask | kStRes)) && ldg) { TVT_FAST_KIND(AMN, BMN, kEpiFast + kSideLdg + (ST)) }                   \
+    TVT_FAST_KIND(AMN, BMN, kEpiFast + (ST))                                                                          \
   }
     TVT_FAST_CASE(false, false, 0)
     TVT_FAST_CASE(false, false, kStRelu)
@@ -913,6 +978,7 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     TVT_FAST_CASE(false, true, kStMask | kStDrop)
     TVT_FAST_CASE(false, true, kStDrop)
 #undef TVT_FAST_CASE
+#undef TVT_FAST_KIND
     ++g_fast_fallbacks;   // no exact kernel for this combination: the generic one below
   }
   return gemm::dispatch_width<1, gemm::kEpiGeneric>(narrow, a, p, s);

@@ -23,27 +23,19 @@ struct FwdParams {
 };
 
 template <typename T, int kChunks>
-__global__ void __launch_bounds__(kWarps * 32) ln_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kWarps * 32, kChunks <= 4 ? 3 : 1) ln_fwd_kernel(const FwdParams p) {
   constexpr int V = Vec16<T>::kN;
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * kWarps;
-  // each lane always owns the same columns: keep their gamma / beta in registers for every row
-  float gam[kChunks][V], bet[kChunks][V];
-#pragma unroll
-  for (int c = 0; c < kChunks; ++c) {
-    const int col = (c * 32 + lane) * V;
-#pragma unroll
-    for (int i = 0; i < V; i += 4) {
-      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
-      if (col < p.d) {
-        g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + i));
-        b4 = __ldg(reinterpret_cast<const float4*>(p.beta + col + i));
-      }
-      gam[c][i] = g4.x; gam[c][i + 1] = g4.y; gam[c][i + 2] = g4.z; gam[c][i + 3] = g4.w;
-      bet[c][i] = b4.x; bet[c][i + 1] = b4.y; bet[c][i + 2] = b4.z; bet[c][i + 3] = b4.w;
-    }
+  // gamma / beta live in shared memory (each lane re-reads its own columns per row, conflict-free): holding them in
+  // registers cost 16 * kChunks registers per thread, and this kernel lives on occupancy (bytes in flight)
+  __shared__ __align__(16) float gam_s[kChunks * 32 * V], bet_s[kChunks * 32 * V];
+  for (int t = threadIdx.x; t < kChunks * 32 * V; t += kWarps * 32) {
+    gam_s[t] = t < p.d ? p.gamma[t] : 0.0f;
+    bet_s[t] = t < p.d ? p.beta[t] : 0.0f;
   }
+  __syncthreads();
   auto src_of = [&](long long row, const float*& pe_row) -> const T* {
     if (p.S > 0) {
       const long long b = row / p.S;
@@ -120,7 +112,14 @@ __global__ void __launch_bounds__(kWarps * 32) ln_fwd_kernel(const FwdParams p) 
       if (col < p.d) {
         float o[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = (v[c][i] - mean) * rstd * gam[c][i] + bet[c][i];
+        for (int i = 0; i < V; i += 4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gam_s + col + i);
+          const float4 b4 = *reinterpret_cast<const float4*>(bet_s + col + i);
+          o[i] = (v[c][i] - mean) * rstd * g4.x + b4.x;
+          o[i + 1] = (v[c][i + 1] - mean) * rstd * g4.y + b4.y;
+          o[i + 2] = (v[c][i + 2] - mean) * rstd * g4.z + b4.z;
+          o[i + 3] = (v[c][i + 3] - mean) * rstd * g4.w + b4.w;
+        }
         Vec16<T>::store(dst + col, o);
       }
     }
@@ -149,22 +148,21 @@ struct BwdParams {
 constexpr int kBwdWarps = 4;
 
 template <typename T, int kChunks>
-__global__ void __launch_bounds__(kBwdWarps * 32) ln_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kBwdWarps * 32, kChunks <= 4 ? 3 : 1) ln_bwd_kernel(const BwdParams p) {
   constexpr int V = Vec16<T>::kN;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long warp0 = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
   const long long nwarps = static_cast<long long>(gridDim.x) * kBwdWarps;
-  float acc_g[kChunks][V], acc_b[kChunks][V], acc_z[kChunks][V], gam[kChunks][V];
+  // Register budget decides this kernel's speed (occupancy = bytes in flight): gamma is re-read from shared memory
+  // and dy * gamma / xhat are recomputed in the second pass instead of being held; what must stay in registers are
+  // the three column accumulators and the packed rows (current + prefetched).
+  __shared__ __align__(16) float gam_s[kChunks * 32 * V];
+  for (int t = threadIdx.x; t < kChunks * 32 * V; t += kBwdWarps * 32) gam_s[t] = t < p.d ? p.gamma[t] : 0.0f;
+  __syncthreads();
+  float acc_g[kChunks][V], acc_b[kChunks][V], acc_z[kChunks][V];
 #pragma unroll
   for (int c = 0; c < kChunks; ++c) {
-    const int col = (c * 32 + lane) * V;
-#pragma unroll
-    for (int i = 0; i < V; i += 4) {
-      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col < p.d) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + i));
-      gam[c][i] = g4.x; gam[c][i + 1] = g4.y; gam[c][i + 2] = g4.z; gam[c][i + 3] = g4.w;
-    }
 #pragma unroll
     for (int i = 0; i < V; ++i) acc_g[c][i] = acc_b[c][i] = acc_z[c][i] = 0.0f;
   }
@@ -194,27 +192,25 @@ __global__ void __launch_bounds__(kBwdWarps * 32) ln_bwd_kernel(const BwdParams 
       }
     }
     const float mean = p.mean[row], rstd = p.rstd[row];
-    float g[kChunks][V], xh[kChunks][V];
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
       const int col = (c * 32 + lane) * V;
       if (col < p.d) {
-        float dyv[V], xv[V];
+        float dyv[V], xv[V], gm[V];
         Vec16<T>::unpack(rdy[c], dyv);
         Vec16<T>::unpack(rx[c], xv);
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          xh[c][i] = (xv[i] - mean) * rstd;
-          acc_g[c][i] += dyv[i] * xh[c][i];
-          acc_b[c][i] += dyv[i];
-          g[c][i] = dyv[i] * gam[c][i];
-          s1 += g[c][i];
-          s2 += g[c][i] * xh[c][i];
-        }
-      } else {
+        for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(gm + i) = *reinterpret_cast<const float4*>(gam_s + col + i);
 #pragma unroll
-        for (int i = 0; i < V; ++i) g[c][i] = xh[c][i] = 0.0f;
+        for (int i = 0; i < V; ++i) {
+          const float xh = (xv[i] - mean) * rstd;
+          acc_g[c][i] += dyv[i] * xh;
+          acc_b[c][i] += dyv[i];
+          const float g = dyv[i] * gm[i];
+          s1 += g;
+          s2 += g * xh;
+        }
       }
     }
     s1 = warp_sum(s1) / p.d;
@@ -232,9 +228,13 @@ __global__ void __launch_bounds__(kBwdWarps * 32) ln_bwd_kernel(const BwdParams 
     for (int c = 0; c < kChunks; ++c) {
       const int col = (c * 32 + lane) * V;
       if (col < p.d) {
-        float o[V];
+        float o[V], dyv[V], xv[V], gm[V];
+        Vec16<T>::unpack(rdy[c], dyv);
+        Vec16<T>::unpack(rx[c], xv);
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+        for (int i = 0; i < V; i += 4) *reinterpret_cast<float4*>(gm + i) = *reinterpret_cast<const float4*>(gam_s + col + i);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = rstd * (dyv[i] * gm[i] - s1 - (xv[i] - mean) * rstd * s2);
         if (p.dres) {
           float rr[V];
           Vec16<T>::load(reinterpret_cast<const T*>(p.dres) + row * p.d + col, rr);

@@ -13,6 +13,7 @@
 
 extern "C" void tvt_debug_set_mn_desc(unsigned lbo, unsigned sbo);
 extern "C" void tvt_debug_set_epilogue(int mode);
+extern "C" void tvt_debug_set_pair(int on);
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
@@ -20,7 +21,8 @@ static float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 static uint32_t rng_state = 12345;
 static float frand() { rng_state = rng_state * 1664525u + 1013904223u; return ((rng_state >> 8) & 0xFFFF) / 32768.0f - 1.0f; }
 
-struct Case { int m, n, k; int amn, bmn, planes, splits; int epi; };  // epi: 0 plain bf16 out, 1 bias+relu+residual, 2 atomic
+struct Case { int m, n, k; int amn, bmn, planes, splits; int epi; };  // epi: 0 plain, 1 bias+relu+residual (both with an fp32 copy: generic kernel), 2 atomic,
+                                                                    //      3 bf16-only bias+residual, 4 bf16-only plain, 5 bf16-only bias+relu (the fast kernels)
 
 static int run_case(const Case& c, bool verbose) {
   const int M = c.m, N = c.n, K = c.k;
@@ -45,7 +47,9 @@ static int run_case(const Case& c, bool verbose) {
   tvt_gemm_args g; memset(&g, 0, sizeof(g));
   g.a = dA; g.b = dB; if (c.planes == 2) { g.a_lo = dAl; g.b_lo = dBl; }
   g.m = M; g.n = N; g.k = K; g.lda = lda; g.ldb = ldb; g.a_mn_major = c.amn; g.b_mn_major = c.bmn; g.splits = c.splits; g.alpha = 1.0f;
-  g.out_f32 = dF; g.ld_f32 = N;
+  if (c.epi < 3) { g.out_f32 = dF; g.ld_f32 = N; } else { g.out_bf16 = dO; g.ld_bf16 = N; }
+  if (c.epi == 3) { g.bias = dBias; g.residual = dR; g.residual_dtype = TVT_BF16; g.ld_residual = N; }
+  if (c.epi == 5) { g.bias = dBias; g.act = TVT_ACT_RELU; }
   if (c.epi == 1) { g.bias = dBias; g.act = TVT_ACT_RELU; g.residual = dR; g.residual_dtype = TVT_BF16; g.ld_residual = N; g.out_bf16 = dO; g.ld_bf16 = N; }
   if (c.epi == 2) g.atomic_out = 1;
   int rc = tvt_gemm(&g, 0);
@@ -53,7 +57,13 @@ static int run_case(const Case& c, bool verbose) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
   std::vector<float> out((size_t)M * N);
-  CK(cudaMemcpy(out.data(), dF, out.size() * 4, cudaMemcpyDeviceToHost));
+  if (c.epi < 3) {
+    CK(cudaMemcpy(out.data(), dF, out.size() * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<__nv_bfloat16> ob((size_t)M * N);
+    CK(cudaMemcpy(ob.data(), dO, ob.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < ob.size(); ++i) out[i] = __bfloat162float(ob[i]);
+  }
   // reference on a sample of rows (all rows when small)
   double max_err = 0, max_ref = 0; int bad = 0;
   const int row_step = M > 512 ? 37 : 1;
@@ -66,11 +76,13 @@ static int run_case(const Case& c, bool verbose) {
         acc += a * b;
       }
       if (c.epi == 1) { acc += bias[j]; if (acc < 0) acc = 0; acc += res[(size_t)i * N + j]; }
+      if (c.epi == 3) acc += bias[j] + res[(size_t)i * N + j];
+      if (c.epi == 5) { acc += bias[j]; if (acc < 0) acc = 0; }
       const double got = out[(size_t)i * N + j];
       const double err = fabs(got - acc);
       if (err > max_err) max_err = err;
       if (fabs(acc) > max_ref) max_ref = fabs(acc);
-      const double tol = (c.planes == 2 ? 2e-4 : 2e-3) * sqrt((double)K) + 1e-3;
+      const double tol = (c.planes == 2 ? 2e-4 : 2e-3) * sqrt((double)K) + 1e-3 + (c.epi >= 3 ? fabs(acc) / 128.0 : 0.0);
       if (!(err <= tol)) { if (bad < 3 && verbose) printf("   mismatch (%d,%d): got %g want %g\n", i, j, got, acc); ++bad; }
     }
   }
@@ -116,6 +128,7 @@ static void bench(int M, int N, int K, int amn, int bmn, int planes, int splits,
 int main(int argc, char** argv) {
   if (tvt_device_check() != 0) { printf("device check failed: %s\n", tvt_last_error()); return 1; }
   if (getenv("TVT_EPI_DBG")) tvt_debug_set_epilogue(atoi(getenv("TVT_EPI_DBG")));
+  if (getenv("TVT_PAIR")) tvt_debug_set_pair(atoi(getenv("TVT_PAIR")));
   if (argc >= 5 && !strcmp(argv[1], "one")) {   // gemm_check one M N K [amn bmn planes splits epi]: a single shape, for ncu
     bench(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 0, argc > 6 ? atoi(argv[6]) : 0,
           argc > 7 ? atoi(argv[7]) : 1, argc > 8 ? atoi(argv[8]) : 1, argc > 9 ? atoi(argv[9]) : 0);
@@ -145,6 +158,10 @@ int main(int argc, char** argv) {
   Case more[] = {{2112, 2048, 512, 0, 1, 1, 1, 0}, {1000, 512, 776, 0, 1, 1, 1, 1}, {768, 3072, 33024, 1, 1, 1, 8, 2}, {512, 2048, 2112, 1, 1, 1, 4, 2},
                  {264, 136, 200, 1, 1, 1, 1, 0}, {512, 512, 2112, 1, 1, 2, 2, 2}, {2112, 512, 2048, 0, 1, 2, 1, 0}, {136, 896, 128, 0, 0, 1, 1, 1}};
   for (auto& c : more) fails += run_case(c, true);
+  // the fast (bf16-only) kernels at sizes that take the CTA-pair path, ragged M included
+  Case fastc[] = {{33024, 768, 768, 0, 0, 1, 1, 3}, {33024, 768, 2048, 0, 0, 1, 1, 3}, {33024, 768, 768, 0, 1, 1, 1, 3}, {33024, 2304, 768, 0, 0, 1, 1, 4},
+                  {33160, 768, 512, 0, 0, 1, 1, 3}, {20000, 1024, 320, 0, 1, 1, 1, 5}, {4000, 512, 256, 0, 0, 1, 1, 5}, {3072, 768, 33024, 1, 1, 1, 2, 2}};
+  for (auto& c : fastc) fails += run_case(c, true);
   printf("gemm_check: %d failing case(s)\n", fails);
   if (argc > 1 && !strcmp(argv[1], "bench")) {
     bench(33024, 768, 768, 0, 0, 1, 1);
