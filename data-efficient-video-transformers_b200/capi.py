@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvt_b200.so")
 
-TVT_BF16, TVT_F32 = 0, 1
+TVT_BF16, TVT_F32, TVT_F64 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 MAX_POOL_SCALES = 8
 MAX_EXPERTS = 8
@@ -126,6 +126,12 @@ class ClsSumArgs(C.Structure):
                 ("num_experts", i32), ("dtype", i32)]
 
 
+class EvalReadoutArgs(C.Structure):
+    _fields_ = [("logits", vp), ("target", vp), ("probs", vp), ("labels", vp), ("pred_bits", vp), ("top1", vp),
+                ("batch", i64), ("classes", i64), ("row_offset", i64), ("capacity", i64),
+                ("thresholds", C.c_float * 16), ("num_thresholds", i32), ("target_dtype", i32)]
+
+
 # entry point -> args Structure (every symbol include/tvt.h declares that takes (args*, stream))
 ENTRY_POINTS = {
     "tvt_gemm": GemmArgs,
@@ -147,6 +153,7 @@ ENTRY_POINTS = {
     "tvt_head_linear_fwd": HeadLinearFwdArgs,
     "tvt_head_linear_bwd": HeadLinearBwdArgs,
     "tvt_cls_sum_fwd": ClsSumArgs,
+    "tvt_eval_readout": EvalReadoutArgs,
 }
 PLAIN_SYMBOLS = ("tvt_last_error", "tvt_version", "tvt_device_check")
 

@@ -599,18 +599,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const uint4 q = lds128(srow + ((((c & 1) * 4 + g) ^ (trow & 7)) << 4));
               side[4 * g] = q.x; side[4 * g + 1] = q.y; side[4 * g + 2] = q.z; side[4 * g + 3] = q.w;
             }
-            if (c & 1) {
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(&sempty_bar[slot]));
-            }
           }
-          if (!live) continue;
+          // the slot is handed back only after its values have been consumed from registers (so the shared-memory
+          // reads are certainly complete before TMA may overwrite the slot)
+          auto release_slot = [&]() {
+            if constexpr (kSide) {
+              if (c & 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sempty_bar[c >> 1]));
+              }
+            }
+          };
+          if (!live) { release_slot(); continue; }
           tmem_ld_wait_dep(r);
-          if ((p.dbg & 3) == 1) continue;
+          if ((p.dbg & 3) == 1) { release_slot(); continue; }
           const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;   // multiple of 8: + q never carries
           uint32_t out[16];
           epilogue_fast<kEpi>(p, scale, bias_addr + c * 128, static_cast<uint32_t>(e4),
                               static_cast<uint32_t>(e4 >> 32) ^ static_cast<uint32_t>(p.dropout_seed >> 32), r, side, out);
+          release_slot();
           if constexpr (side_ldg(kEpi)) {
             if (c + 1 < BN / 64 && col0 + 32 < p.N && row < p.M) { ldg256(side_row + col0 + 32, side); ldg256(side_row + col0 + 48, side + 8); }
           }

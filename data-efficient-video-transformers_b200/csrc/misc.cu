@@ -441,3 +441,64 @@ extern "C" int tvt_cls_sum_fwd(const tvt_cls_sum_args* a, void* stream) {
   else misc::cls_sum_kernel<__nv_bfloat16><<<misc::grid1d(items, 256), 256, 0, s>>>(p);
   return check_launch("tvt_cls_sum_fwd");
 }
+
+// ---------------------------------------------------------------------------------------- evaluation read-out
+namespace tvt {
+namespace misc {
+struct EvalParams {
+  const float* logits; const void* target; float* probs; int32_t* labels; uint16_t* bits; int32_t* top1;
+  long long B, C, row0; int nthr, tgt_f64; float thr[TVT_MAX_THRESHOLDS];
+};
+// one warp per clip: lanes stride over the classes, then a warp argmax (lowest index among equal maxima)
+__global__ void __launch_bounds__(256) eval_readout_kernel(const EvalParams p) {
+  const long long b = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (b >= p.B) return;
+  const int lane = threadIdx.x & 31;
+  const long long orow = (p.row0 + b) * p.C;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int c = lane; c < p.C; c += 32) {
+    const float z = p.logits[b * p.C + c];
+    const float pr = 1.0f / (1.0f + expf(-z));
+    p.probs[orow + c] = pr;
+    if (p.labels && p.target)
+      p.labels[orow + c] = p.tgt_f64 ? static_cast<int32_t>(reinterpret_cast<const double*>(p.target)[b * p.C + c])
+                                     : static_cast<int32_t>(reinterpret_cast<const float*>(p.target)[b * p.C + c]);
+    if (p.bits) {
+      unsigned m = 0;
+      for (int k = 0; k < p.nthr; ++k) m |= (pr > p.thr[k] ? 1u : 0u) << k;
+      p.bits[orow + c] = static_cast<uint16_t>(m);
+    }
+    if (z > best || (z != z && best == best)) { best = z; besti = c; }   // NaN counts as the maximum, like torch.argmax
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    const bool take = (ob > best) || (ob != ob && best == best) || (ob == best && oi < besti) || (ob != ob && best != best && oi < besti);
+    if (take) { best = ob; besti = oi; }
+  }
+  if (lane == 0 && p.top1) p.top1[p.row0 + b] = besti;
+}
+}  // namespace misc
+}  // namespace tvt
+
+extern "C" int tvt_eval_readout(const tvt_eval_readout_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->logits && a->probs, "tvt_eval_readout: null pointer");
+  TVT_REQUIRE(a->batch >= 0 && a->classes > 0, "tvt_eval_readout: bad shape");
+  TVT_REQUIRE(a->row_offset >= 0 && a->row_offset + a->batch <= a->capacity,
+              "tvt_eval_readout: rows [%lld, %lld) exceed the running buffer's capacity %lld", (long long)a->row_offset,
+              (long long)(a->row_offset + a->batch), (long long)a->capacity);
+  TVT_REQUIRE(a->num_thresholds >= 0 && a->num_thresholds <= TVT_MAX_THRESHOLDS, "tvt_eval_readout: too many thresholds");
+  TVT_REQUIRE(!a->target || a->target_dtype == TVT_F32 || a->target_dtype == TVT_F64, "tvt_eval_readout: target must be f32 or f64");
+  if (a->batch == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  misc::EvalParams p{};
+  p.logits = a->logits; p.target = a->target; p.probs = a->probs; p.labels = a->labels; p.bits = a->pred_bits; p.top1 = a->top1;
+  p.B = a->batch; p.C = a->classes; p.row0 = a->row_offset; p.nthr = a->num_thresholds; p.tgt_f64 = a->target_dtype == TVT_F64;
+  for (int k = 0; k < a->num_thresholds; ++k) p.thr[k] = a->thresholds[k];
+  misc::eval_readout_kernel<<<static_cast<unsigned>((a->batch + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("tvt_eval_readout");
+}

@@ -1,0 +1,106 @@
+"""Evaluation path: the step after the hot path.
+
+The reference's ``validation_step`` (src/models/transformer.py:146-158) appends ``sigmoid(logits)``, the raw logits and
+``target.int()`` to Python lists, and its callback (src/callbacks/callbacks.py:34-45) concatenates them, moves them to the
+host and thresholds them once per threshold in ``[0, 0.1 ... 0.8]`` for sklearn.  Here
+
+* ``EvalBuffer`` is ONE preallocated device buffer per quantity that every batch is written into by a single kernel
+  launch (``tvt_eval_readout``: sigmoid, label cast, all thresholds as a bit mask, top-1 index); the sklearn metrics
+  stay on the CPU and read one contiguous ``[N, C]`` array per quantity;
+* ``GraphedForward`` captures the inference-only forward of a module (no saved activations, dropout off) in a CUDA
+  graph, so the launch-bound small configurations (BASELINE C1-C3) replay ~100 kernels with one launch.
+"""
+import torch
+
+from .. import ops
+
+REFERENCE_THRESHOLDS = (0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8)   # callbacks.py:37
+
+
+class EvalBuffer:
+    """Running evaluation buffers on the device: ``probs`` [N, C] fp32, ``labels`` [N, C] int32, ``pred_bits`` [N, C]
+    (bit k: prob > thresholds[k]) and ``top1`` [N]; ``append`` is one kernel launch per batch."""
+
+    def __init__(self, capacity, n_classes, thresholds=REFERENCE_THRESHOLDS, device="cuda"):
+        if len(thresholds) > 16:
+            raise ValueError("EvalBuffer: at most 16 thresholds")
+        self.capacity, self.n_classes, self.thresholds = int(capacity), int(n_classes), tuple(float(t) for t in thresholds)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("EvalBuffer lives on a CUDA device: this path has no CPU implementation")
+        self._probs = torch.zeros(self.capacity, self.n_classes, dtype=torch.float32, device=dev)
+        self._labels = torch.zeros(self.capacity, self.n_classes, dtype=torch.int32, device=dev)
+        self._bits = torch.zeros(self.capacity, self.n_classes, dtype=torch.int16, device=dev)
+        self._top1 = torch.zeros(self.capacity, dtype=torch.int32, device=dev)
+        self.rows = 0
+
+    def reset(self):
+        self.rows = 0
+
+    def append(self, logits, target=None):
+        """logits [B, C] (any float dtype), target [B, C] or [B, 1, C] float (the loader's layout) or None."""
+        logits = logits.detach().reshape(-1, self.n_classes).float().contiguous()
+        if target is not None:
+            target = target.detach().reshape(-1, self.n_classes)
+            if target.dtype not in (torch.float32, torch.float64):
+                target = target.float()
+            if target.shape[0] != logits.shape[0]:
+                raise ValueError(f"EvalBuffer.append: {logits.shape[0]} logit rows but {target.shape[0]} target rows")
+            target = target.to(logits.device)
+        if self.rows + logits.shape[0] > self.capacity:
+            raise ValueError(f"EvalBuffer.append: {self.rows} + {logits.shape[0]} rows exceed the capacity {self.capacity}")
+        ops.eval_readout(logits, target, self._probs, self._labels, self._bits, self._top1, self.rows, self.thresholds)
+        self.rows += logits.shape[0]
+
+    # views of the filled part
+    @property
+    def probs(self):
+        return self._probs[: self.rows]
+
+    @property
+    def labels(self):
+        return self._labels[: self.rows]
+
+    @property
+    def top1(self):
+        return self._top1[: self.rows]
+
+    def predictions(self, threshold):
+        """(probs > threshold) as int32 [N, C] for one of the configured thresholds."""
+        k = self.thresholds.index(float(threshold))
+        return ((self._bits[: self.rows].to(torch.int32) >> k) & 1)
+
+    def to_host(self):
+        """The arrays the reference's callback hands to sklearn, each with ONE device-to-host copy."""
+        return {"probs": self.probs.cpu().numpy(), "labels": self.labels.cpu().numpy(), "top1": self.top1.cpu().numpy(),
+                "pred_bits": self._bits[: self.rows].cpu().numpy()}
+
+
+class GraphedForward:
+    """CUDA-graph replay of ``fn(*inputs)`` for fixed input shapes, inference only (``torch.no_grad``; put the module in
+    ``eval()`` first - a captured graph would replay the same dropout seeds).  ``fn`` may return a tensor or a tuple /
+    list of tensors; the returned tensors are static buffers overwritten by the next call."""
+
+    def __init__(self, fn, example_inputs, warmup=2):
+        self.fn = fn
+        self.static_in = [x.clone() for x in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):          # lazy initialisation (kernel attributes, weight plane caches) stays out of the graph
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        if len(inputs) != len(self.static_in):
+            raise ValueError(f"GraphedForward: expected {len(self.static_in)} inputs, got {len(inputs)}")
+        for dst, src in zip(self.static_in, inputs):
+            if dst.shape != src.shape:
+                raise ValueError(f"GraphedForward: captured for input shape {tuple(dst.shape)}, got {tuple(src.shape)}")
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

@@ -394,3 +394,26 @@ def pyramid_head(z, target=None, need_grad=False, grad_scale=1.0):
     a = capi.PyramidHeadArgs(_p(z), _p(target), _p(prob), _p(loss), _p(dz), G, B, Cc, grad_scale)
     capi.call("tvt_pyramid_head", a, _stream())
     return prob, loss, dz
+
+
+def eval_readout(logits, target, probs, labels, pred_bits, top1, row_offset, thresholds):
+    """Evaluation read-out of one batch into caller-owned running buffers (tvt_eval_readout; reference:
+    src/models/transformer.py:146-158 + src/callbacks/callbacks.py:34-45).  logits [B, C] fp32; target [B, C] fp32 /
+    fp64 or None; probs / labels / pred_bits are [capacity, C], top1 is [capacity]."""
+    _cuda(logits, probs)
+    if logits.dtype != torch.float32 or not logits.is_contiguous():
+        raise ValueError("eval_readout: logits must be contiguous fp32")
+    if target is not None and target.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"eval_readout: target must be float32 or float64 (got {target.dtype})")
+    if len(thresholds) > 16:
+        raise ValueError("eval_readout: at most 16 thresholds")
+    B, C = logits.shape
+    a = capi.EvalReadoutArgs()
+    a.logits, a.target, a.probs = _p(logits), _p(target.contiguous() if target is not None else None), _p(probs)
+    a.labels, a.pred_bits, a.top1 = _p(labels), _p(pred_bits), _p(top1)
+    a.batch, a.classes, a.row_offset, a.capacity = B, C, row_offset, probs.shape[0]
+    for i, t in enumerate(thresholds):
+        a.thresholds[i] = float(t)
+    a.num_thresholds = len(thresholds)
+    a.target_dtype = capi.TVT_F64 if (target is not None and target.dtype == torch.float64) else TVT_F32
+    capi.call("tvt_eval_readout", a, _stream())

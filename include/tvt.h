@@ -37,7 +37,7 @@ typedef enum {
   TVT_ECUDA = -4       /* CUDA runtime / driver error, see tvt_last_error() */
 } tvt_status;
 
-typedef enum { TVT_BF16 = 0, TVT_F32 = 1 } tvt_dtype;
+typedef enum { TVT_BF16 = 0, TVT_F32 = 1, TVT_F64 = 2 /* evaluation labels only */ } tvt_dtype;
 typedef enum { TVT_ACT_NONE = 0, TVT_ACT_RELU = 1, TVT_ACT_GELU = 2 } tvt_act;
 
 TVT_API const char* tvt_last_error(void);
@@ -403,6 +403,28 @@ typedef struct {
   int32_t dtype;
 } tvt_cls_sum_args;
 TVT_API int tvt_cls_sum_fwd(const tvt_cls_sum_args* args, void* stream);
+
+/* Evaluation read-out (src/models/transformer.py:146-158 validation_step + src/callbacks/callbacks.py:34-45): one pass
+ * over a batch of logits that appends, at row `row_offset` of caller-owned running buffers of `capacity` rows,
+ *   probs = sigmoid(logits)            (what the reference appends to running_logits),
+ *   labels = (int)target               (target.int(), appended to running_labels),
+ *   pred_bits: bit k set iff probs > thresholds[k]   (the callback's (running_logits > t) for its list of thresholds),
+ *   top1 = argmax_c logits             (first maximum, torch.argmax tie rule).
+ * Replaces the reference's Python lists of per-batch tensors + torch.cat + one elementwise pass per threshold. */
+#define TVT_MAX_THRESHOLDS 16
+typedef struct {
+  const float* logits;       /* [batch, classes] */
+  const void* target;        /* [batch, classes], target_dtype; may be NULL (labels untouched) */
+  float* probs;              /* [capacity, classes] */
+  int32_t* labels;           /* [capacity, classes] or NULL */
+  uint16_t* pred_bits;       /* [capacity, classes] or NULL */
+  int32_t* top1;             /* [capacity] or NULL */
+  int64_t batch, classes, row_offset, capacity;
+  float thresholds[TVT_MAX_THRESHOLDS];
+  int32_t num_thresholds;
+  int32_t target_dtype;      /* TVT_F32 or TVT_F64 */
+} tvt_eval_readout_args;
+TVT_API int tvt_eval_readout(const tvt_eval_readout_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -351,3 +351,14 @@ def distill_loss(student, teacher, target, temperature=0.0, alpha=0.0, pyramid=N
         parts["pyramid"] = pb
         loss = loss + pb
     return loss, parts
+
+
+def eval_readout(logits, target, thresholds=(0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8)):
+    """What the reference's evaluation path produces per batch: ``F.sigmoid(data)`` and ``target.int()``
+    (src/models/transformer.py:150-153), ``(running_logits > threshold).to(int)`` for the callback's thresholds
+    (src/callbacks/callbacks.py:37-40), plus the arg-max class used by the top-1 agreement criterion."""
+    logits = logits.float()
+    probs = torch.sigmoid(logits)
+    labels = None if target is None else target.reshape(logits.shape).int()
+    preds = [(probs > t).int() for t in thresholds]
+    return probs, labels, preds, torch.argmax(logits, dim=-1)

@@ -401,3 +401,64 @@ def test_full_size_properties(api):
     assert torch.equal(c, a[perm]) and close(pc, pa[perm])                 # clip independence
     assert torch.equal(d_, a) and close(pd_, pa)                           # dropout-free train == eval
     assert torch.isfinite(a).all() and float(pa.min()) >= 0.0 and float(pa.max()) <= 1.0
+
+
+def test_eval_buffer_matches_reference_eval_path(api):
+    """Evaluation read-out (transformer.py:146-158, callbacks.py:34-45): sigmoid / label cast / per-threshold
+    predictions / top-1 from ONE launch per batch into running device buffers, against the oracle restatement.
+    Integer outputs are exact; a thresholded bit may only differ where the probability sits on the threshold."""
+    from oracle import param
+    gen = torch.Generator().manual_seed(1130)
+    C = 19
+    buf = api.EvalBuffer(capacity=700, n_classes=C)
+    all_logits, all_tgt = [], []
+    for B in (256, 1, 300, 37):                                # ragged batches, the last one partial
+        logits = torch.randn(B, C, generator=gen) * 3.0
+        logits[0, 3] = logits[0, 7] = logits[0].max() + 1.0     # a tie: torch.argmax takes the first
+        tgt = _targets(B, C, gen).double().reshape(B, 1, C)     # the loader's [B, 1, C] float64 labels
+        buf.append(logits.to(DEV), tgt.to(DEV))
+        all_logits.append(logits)
+        all_tgt.append(tgt)
+    logits, tgt = torch.cat(all_logits), torch.cat(all_tgt)
+    probs, labels, preds, top1 = param.eval_readout(logits, tgt)
+    assert buf.rows == 594 and buf.probs.shape == (594, C)
+    assert_close(buf.probs.cpu(), probs, 1e-6, "probs")
+    assert torch.equal(buf.labels.cpu(), labels)
+    assert torch.equal(buf.top1.cpu().long(), top1)
+    for t, ref in zip(api.REFERENCE_THRESHOLDS, preds):
+        got = buf.predictions(t).cpu()
+        off = (got != ref) & ((probs - t).abs() > 1e-6)
+        assert not off.any(), f"threshold {t}: {int(off.sum())} predictions differ away from the threshold"
+    host = buf.to_host()
+    assert host["probs"].shape == (594, C) and host["labels"].dtype.name == "int32"
+    with pytest.raises(ValueError):
+        buf.append(torch.zeros(200, C, device=DEV))             # would overflow the capacity
+    buf.reset()
+    assert buf.rows == 0 and buf.probs.shape[0] == 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_inference_forward_is_bit_identical(api, precision):
+    """The CUDA-graph replay of the inference-only forward returns exactly what the eager forward returns, for
+    fresh inputs after capture, and matches the oracle within the precision's tolerance."""
+    from oracle import param
+    B = 8
+    cfg = dict(batch_size=B, seq_len=16, cls=1, dropout=0.5, input_dimension=256, nhead=4, nhid=512, nlayers=2,
+               model="ptn", learning_rate=1e-3, momentum=0.0, weight_decay=0.0, n_classes=15)
+    torch.manual_seed(1130)
+    ref = param.SimpleTransformer(**cfg).to(DEV).eval()
+    mod = copy_state(api.SimpleTransformer(precision=precision, **cfg), ref).to(DEV).eval()
+    gen = torch.Generator().manual_seed(7)
+    x0 = torch.randn(B, 16, 3, 256, generator=gen).to(DEV)
+    graphed = api.GraphedForward(mod.ptn, [x0])
+    for _ in range(3):
+        x = torch.randn(B, 16, 3, 256, generator=gen).to(DEV)
+        with torch.no_grad():
+            eager = mod.ptn(x).clone()
+            want = ref.ptn(x)
+        got = graphed(x)
+        torch.cuda.synchronize()
+        assert torch.equal(got, eager)
+        assert_close(got, want, TOL[precision], "graphed logits")
+    with pytest.raises(ValueError):
+        graphed(torch.zeros(B + 1, 16, 3, 256, device=DEV))
