@@ -139,12 +139,12 @@ __global__ void __launch_bounds__(256) optim_kernel(const OptParams a) {
       const float4 m4 = *reinterpret_cast<const float4*>(a.m + i);
       p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w; g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
       m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
-      if (a.kind == 0) { const float4 v4 = *reinterpret_cast<const float4*>(a.v + i); v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w; }
+      if (a.kind != 1) { const float4 v4 = *reinterpret_cast<const float4*>(a.v + i); v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w; }
     } else {
       for (int j = 0; j < 4; ++j) {
         const bool ok = i + j < a.n;
         p[j] = ok ? a.p[i + j] : 0.f; g[j] = ok ? a.g[i + j] : 0.f; m[j] = ok ? a.m[i + j] : 0.f;
-        v[j] = ok && a.kind == 0 ? a.v[i + j] : 0.f;
+        v[j] = ok && a.kind != 1 ? a.v[i + j] : 0.f;
       }
     }
 #pragma unroll
@@ -156,16 +156,20 @@ __global__ void __launch_bounds__(256) optim_kernel(const OptParams a) {
         v[j] = a.b2 * v[j] + (1.0f - a.b2) * gj * gj;
         const float denom = sqrtf(v[j]) * a.bc2_rsqrt + a.eps;
         p[j] -= a.lr * a.bc1_inv * (m[j] / denom);
-      } else {
+      } else if (a.kind == 1) {
         gj += a.wd * p[j];
         m[j] = a.first ? gj : a.mom * m[j] + gj;
         p[j] -= a.lr * m[j];
+      } else {   // Adagrad (torch.optim.Adagrad, lr_decay = 0, initial accumulator 0): v is the running sum of g^2
+        gj += a.wd * p[j];
+        v[j] += gj * gj;
+        p[j] -= a.lr * gj / (sqrtf(v[j]) + a.eps);
       }
     }
     if (full) {
       *reinterpret_cast<float4*>(a.p + i) = make_float4(p[0], p[1], p[2], p[3]);
       *reinterpret_cast<float4*>(a.m + i) = make_float4(m[0], m[1], m[2], m[3]);
-      if (a.kind == 0) *reinterpret_cast<float4*>(a.v + i) = make_float4(v[0], v[1], v[2], v[3]);
+      if (a.kind != 1) *reinterpret_cast<float4*>(a.v + i) = make_float4(v[0], v[1], v[2], v[3]);
       if (a.hi) {
         float h[4];
 #pragma unroll
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(256) optim_kernel(const OptParams a) {
     } else {
       for (int j = 0; j < 4 && i + j < a.n; ++j) {
         a.p[i + j] = p[j]; a.m[i + j] = m[j];
-        if (a.kind == 0) a.v[i + j] = v[j];
+        if (a.kind != 1) a.v[i + j] = v[j];
         if (a.hi) {
           const __nv_bfloat16 h = __float2bfloat16_rn(p[j]);
           a.hi[i + j] = h;
@@ -361,8 +365,8 @@ extern "C" int tvt_act_bwd(const tvt_act_bwd_args* a, void* stream) {
 extern "C" int tvt_optim_step(const tvt_optim_step_args* a, void* stream) {
   using namespace tvt;
   TVT_REQUIRE(a != nullptr && a->p && a->g && a->m, "tvt_optim_step: null pointer");
-  TVT_REQUIRE(a->kind == 0 || a->kind == 1, "tvt_optim_step: kind must be 0 (AdamW) or 1 (SGD)");
-  TVT_REQUIRE(a->kind == 1 || a->v, "tvt_optim_step: AdamW needs the second-moment buffer");
+  TVT_REQUIRE(a->kind >= 0 && a->kind <= 2, "tvt_optim_step: kind must be 0 (AdamW), 1 (SGD) or 2 (Adagrad)");
+  TVT_REQUIRE(a->kind == 1 || a->v, "tvt_optim_step: AdamW / Adagrad need the second-moment buffer");
   TVT_REQUIRE(a->n >= 0 && a->step >= 1, "tvt_optim_step: bad n / step");
   TVT_REQUIRE(al16(a->p) && al16(a->g) && al16(a->m) && al16(a->v) && (reinterpret_cast<uintptr_t>(a->p_hi) & 7) == 0 &&
                   (reinterpret_cast<uintptr_t>(a->p_lo) & 7) == 0,

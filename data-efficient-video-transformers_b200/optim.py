@@ -1,10 +1,10 @@
-"""Flat-bucket optimizer: AdamW / SGD-momentum applied by ONE kernel launch per
+"""Flat-bucket optimizer: AdamW / SGD-momentum / Adagrad applied by ONE kernel launch per
 gradient bucket.  Parameters are re-pointed to views of a flat fp32 buffer laid out exactly like the
 ``GradBucketReducer``'s gradient buckets, so the step is a perfectly coalesced pass that also
   * applies the data-parallel gradient averaging (1 / world), and
   * writes the bf16 operand planes the next step's GEMMs read (registered in the modules' ``ops.Mode`` caches),
 replacing torch's multi-tensor optimizer, the bucket scaling pass and ~60 per-weight conversion launches.
-Update rules and defaults are torch.optim.AdamW's / torch.optim.SGD's (the reference's configure_optimizers:
+Update rules and defaults are torch.optim.AdamW's / SGD's / Adagrad's (the reference's configure_optimizers:
 src/models/frame_transformer.py:123-134, src/models/transformer.py:58-64)."""
 import weakref
 
@@ -15,10 +15,10 @@ from . import capi, ops
 
 class FlatOptimizer:
     def __init__(self, reducer, modes=(), kind="adamw", lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, momentum=0.0):
-        if kind not in ("adamw", "sgd"):
-            raise ValueError("kind must be 'adamw' or 'sgd'")
+        if kind not in ("adamw", "sgd", "adagrad"):
+            raise ValueError("kind must be 'adamw', 'sgd' or 'adagrad'")
         self.reducer, self.modes = reducer, list(modes)
-        self.kind = 0 if kind == "adamw" else 1
+        self.kind = {"adamw": 0, "sgd": 1, "adagrad": 2}[kind]
         self.lr, self.betas, self.eps, self.weight_decay, self.momentum = lr, betas, eps, weight_decay, momentum
         self.step_count = 0
         self.buckets = []
@@ -35,7 +35,7 @@ class FlatOptimizer:
             hi = torch.empty(flat_g.numel(), dtype=torch.bfloat16, device=flat_g.device) if self.modes else None
             lo = torch.empty_like(hi) if (hi is not None and want_lo) else None
             self.buckets.append({"p": flat_p, "g": flat_g, "m": torch.zeros_like(flat_g),
-                                 "v": torch.zeros_like(flat_g) if self.kind == 0 else None, "hi": hi, "lo": lo, "views": views})
+                                 "v": torch.zeros_like(flat_g) if self.kind != 1 else None, "hi": hi, "lo": lo, "views": views})
 
     def zero_grad(self):
         self.reducer.zero_grad()

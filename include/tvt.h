@@ -357,6 +357,7 @@ TVT_API int tvt_act_bwd(const tvt_act_bwd_args* args, void* stream);
  *   kind 0 (AdamW): p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
  *                   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
  *   kind 1 (SGD):   g += wd * p;  buf = momentum * buf + g  (buf = g on the first step);  p -= lr * buf
+ *   kind 2 (Adagrad, src/models/frame_transformer.py:131-133): g += wd * p;  v += g^2;  p -= lr * g / (sqrt(v) + eps)
  * All arrays fp32 of n elements; `m` is the first-moment / momentum buffer, `v` unused for SGD. */
 typedef struct {
   float* p;

@@ -140,12 +140,30 @@ def case_frame_stream(ref):
     return {"logits": out_ref.detach(), "teacher": teacher, "target": target, "loss": (base + distil).detach(), "cos": cos.detach()}
 
 
+def case_collab(ref):
+    """src/models/collabgating.py on its own nested-list input layout against the stacked-row restatement."""
+    torch.manual_seed(SEED)
+    c_ref = ref.collab.CollaborativeGating().eval()
+    torch.manual_seed(SEED)
+    c_or = param.CollaborativeGating().eval()
+    for (na, a), (nb, b) in zip(c_ref.state_dict().items(), c_or.state_dict().items()):
+        assert na == nb and torch.equal(a, b), (na, nb)
+    g = torch.Generator().manual_seed(SEED)
+    B, S, dims = 2, 3, (2048, 1024, 128)
+    xs = [torch.randn(B, S, D, generator=g) for D in dims]
+    nested = [[[x[b, s].reshape(1, -1) for x in xs] for s in range(S)] for b in range(B)]
+    with torch.no_grad():
+        o_ref, o_or = c_ref(nested), c_or(xs)
+    assert o_ref.shape == (B, S, 1024) and torch.allclose(o_ref, o_or, atol=2e-6), float((o_ref - o_or).abs().max())
+    return {"xs": xs, "out": o_ref.detach()}
+
+
 def main():
     if not ref_loader.available():
         sys.exit("reference not available: golden vectors can only be regenerated where /root/reference exists")
     ref = ref_loader.load()
     gold = {"seed": SEED, "torch": torch.__version__}
-    for fn in (case_ptn, case_posenc, case_reasoning, case_vit, case_spatial_pyramid, case_frame_stream):
+    for fn in (case_ptn, case_posenc, case_reasoning, case_vit, case_spatial_pyramid, case_frame_stream, case_collab):
         gold[fn.__name__[5:]] = fn(ref)
         print("ok", fn.__name__)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

@@ -362,3 +362,55 @@ def eval_readout(logits, target, thresholds=(0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 
     labels = None if target is None else target.reshape(logits.shape).int()
     preds = [(probs > t).int() for t in thresholds]
     return probs, labels, preds, torch.argmax(logits, dim=-1)
+
+
+class GatedEmbeddingUnit(nn.Module):
+    """src/models/collabgating.py:59-70: Linear then L2 normalisation along dim 1 (its context gate is commented out)."""
+
+    def __init__(self, input_dimension, output_dimension, use_bn=False):
+        super().__init__()
+        self.fc = nn.Linear(input_dimension, output_dimension)
+
+    def forward(self, x):
+        return F.normalize(self.fc(x))
+
+
+class CollaborativeGating(nn.Module):
+    """Restatement of src/models/collabgating.py:3-56 on stacked rows instead of nested Python lists.
+
+    Reference input: list (batch) of list (scenes) of list (experts) of ``[1, D_e]`` tensors; here ``xs`` is a list over
+    experts of ``[B, S, D_e]`` tensors and the result is the reference's ``[B, S, 1024]``.  Per (clip, scene), with
+    P = ``projection`` (ONE shared Linear(2048, 2048), :9) and the work list L = [x_0 .. x_{E-1}]:
+      for i in range(E):  cur = L.pop(0); c = P(pad(cur))                                   (:28-33)
+                          t = sum_{o in L} (c + P(pad(o)))                                   (:35-43)
+                          out_i = GLU(cat(c, c + P(t))) = c * sigmoid(c + P(t))              (:45-47, :83-85)
+                          L.append(c)      <- the PROJECTED vector: later iterations project it again  (:49)
+      result = normalize(geu.fc(sum_i out_i))                                                (:50-53, :66-69)
+    ``pad`` is nearest-neighbour ``F.interpolate`` to 2048 for any expert whose width differs (:12-16).  E >= 2 (the
+    reference stacks an empty list for a single expert)."""
+
+    def __init__(self):
+        super().__init__()
+        self.proj_input = 2048
+        self.proj_embedding_size = 2048
+        self.projection = nn.Linear(self.proj_input, self.proj_embedding_size)
+        self.geu = GatedEmbeddingUnit(self.proj_input, 1024, False)
+
+    def pad(self, x):
+        if x.shape[-1] == self.proj_input:
+            return x
+        return F.interpolate(x.reshape(-1, 1, x.shape[-1]), self.proj_input).reshape(*x.shape[:-1], self.proj_input)
+
+    def forward(self, xs):
+        if len(xs) < 2:
+            raise ValueError("CollaborativeGating needs at least two experts")
+        work = list(xs)
+        total = None
+        for _ in range(len(xs)):
+            c = self.projection(self.pad(work.pop(0)))
+            t = sum(c + self.projection(self.pad(o)) for o in work)
+            gated = c * torch.sigmoid(c + self.projection(t))
+            total = gated if total is None else total + gated
+            work.append(c)
+        B, S = total.shape[:2]
+        return self.geu(total.reshape(B * S, -1)).reshape(B, S, -1)

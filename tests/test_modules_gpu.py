@@ -462,3 +462,28 @@ def test_graphed_inference_forward_is_bit_identical(api, precision):
         assert_close(got, want, TOL[precision], "graphed logits")
     with pytest.raises(ValueError):
         graphed(torch.zeros(B + 1, 16, 3, 256, device=DEV))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_collaborative_gating_parity(api, precision):
+    """Collaborative gating (collabgating.py:3-56) as three stacked tensor-core GEMMs against the oracle (which is
+    pinned to the unmodified reference class by tests/golden): forward on the stacked and on the reference's nested
+    list layout, and every parameter gradient."""
+    from oracle import param
+    torch.manual_seed(1130)
+    ref = param.CollaborativeGating().to(DEV)
+    mod = copy_state(api.CollaborativeGating(precision=precision), ref).to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    B, S = (4, 3) if precision == "fp32" else (16, 8)
+    xs = [torch.randn(B, S, D, generator=gen).to(DEV) for D in (2048, 1024, 128)]
+    w = torch.randn(B, S, 1024, generator=gen).to(DEV)
+    out_ref = ref(xs)
+    (out_ref * w).sum().backward()
+    out = mod(xs)
+    (out * w).sum().backward()
+    assert_close(out, out_ref, TOL[precision], "collab out")
+    nested = [[[x[b, s].reshape(1, -1) for x in xs] for s in range(S)] for b in range(B)]
+    with torch.no_grad():
+        assert torch.equal(mod(nested), mod(xs))
+    yard = _yardstick(ref, precision, lambda m: (_ac(lambda: m(xs)).float() * w).sum())
+    grads_close(mod, ref, TOL[precision], "collab ", yard=yard)
