@@ -126,6 +126,11 @@ class ClsSumArgs(C.Structure):
                 ("num_experts", i32), ("dtype", i32)]
 
 
+class FeatureAugmentArgs(C.Structure):
+    _fields_ = [("x", vp), ("y", vp), ("rows", i64), ("d_in", i64), ("d_out", i64), ("p_drop", C.c_float), ("p_noise", C.c_float),
+                ("noise_std", C.c_float), ("seed", C.c_uint64), ("out_dtype", i32)]
+
+
 class EvalReadoutArgs(C.Structure):
     _fields_ = [("logits", vp), ("target", vp), ("probs", vp), ("labels", vp), ("pred_bits", vp), ("top1", vp),
                 ("batch", i64), ("classes", i64), ("row_offset", i64), ("capacity", i64),
@@ -154,6 +159,7 @@ ENTRY_POINTS = {
     "tvt_head_linear_bwd": HeadLinearBwdArgs,
     "tvt_cls_sum_fwd": ClsSumArgs,
     "tvt_eval_readout": EvalReadoutArgs,
+    "tvt_feature_augment": FeatureAugmentArgs,
 }
 PLAIN_SYMBOLS = ("tvt_last_error", "tvt_version", "tvt_device_check")
 

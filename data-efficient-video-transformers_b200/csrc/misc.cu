@@ -506,3 +506,74 @@ extern "C" int tvt_eval_readout(const tvt_eval_readout_args* a, void* stream) {
   misc::eval_readout_kernel<<<static_cast<unsigned>((a->batch + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("tvt_eval_readout");
 }
+
+// ---------------------------------------------------------------------------------------- loader augmentation
+namespace tvt {
+namespace misc {
+constexpr uint32_t kAugNoiseStream = 0x6E6F6973u;   // xor'ed into the seed's high word for the per-element stream
+__device__ __forceinline__ float aug_u01(uint32_t w) { return (static_cast<float>(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1)
+
+template <typename T>
+__global__ void __launch_bounds__(256) feature_augment_kernel(const float* x, T* y, long long rows, int d_in, int d_out, float p_drop,
+                                                              float p_noise, float noise_std, unsigned long long seed) {
+  uint32_t rk[kDropoutRounds], rkn[kDropoutRounds];
+#pragma unroll
+  for (int r = 0; r < kDropoutRounds; ++r) rk[r] = rkn[r] = static_cast<uint32_t>(seed) + r * kDropoutWeyl;
+  const uint32_t hi_row = static_cast<uint32_t>(seed >> 32), hi_noise = hi_row ^ kAugNoiseStream;
+  const int q_per_row = d_out / 4;
+  const long long total = rows * q_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / q_per_row;
+    const int c = static_cast<int>(i - row * q_per_row) * 4;
+    uint32_t w0, w1;
+    dropout_words(rk, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32) ^ hi_row, w0, w1);
+    const bool drop = aug_u01(w0) < p_drop, noise = aug_u01(w1) < p_noise;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!drop && c < d_in) {
+      const float4 a = *reinterpret_cast<const float4*>(x + row * d_in + c);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    if (noise) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {   // one hash -> one Box-Muller pair -> columns c + 2h, c + 2h + 1
+        const unsigned long long ctr = static_cast<unsigned long long>(row) * (d_out / 2) + (c >> 1) + h;
+        uint32_t a, b;
+        dropout_words(rkn, static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32) ^ hi_noise, a, b);
+        const float rad = sqrtf(-2.0f * logf(aug_u01(a))) * noise_std;
+        float sn, cs;
+        sincosf(6.283185307179586f * aug_u01(b), &sn, &cs);
+        v[2 * h] += rad * cs;
+        v[2 * h + 1] += rad * sn;
+      }
+    }
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * d_out + c) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * d_out + c) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
+  }
+}
+}  // namespace misc
+}  // namespace tvt
+
+extern "C" int tvt_feature_augment(const tvt_feature_augment_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->x && a->y, "tvt_feature_augment: null pointer");
+  TVT_REQUIRE(a->rows >= 0 && a->d_in > 0 && a->d_out >= a->d_in && a->d_in % 4 == 0 && a->d_out % 4 == 0,
+              "tvt_feature_augment: need 0 < d_in <= d_out, both multiples of 4 (got %lld, %lld)", (long long)a->d_in, (long long)a->d_out);
+  TVT_REQUIRE(a->d_out < (1ll << 31), "tvt_feature_augment: d_out exceeds int32");
+  TVT_REQUIRE(a->p_drop >= 0.0f && a->p_drop <= 1.0f && a->p_noise >= 0.0f && a->p_noise <= 1.0f && a->noise_std >= 0.0f,
+              "tvt_feature_augment: probabilities must be in [0, 1] and noise_std >= 0");
+  TVT_REQUIRE(a->out_dtype == TVT_BF16 || a->out_dtype == TVT_F32, "tvt_feature_augment: bad out_dtype");
+  TVT_REQUIRE(al16(a->x) && al16(a->y), "tvt_feature_augment: pointers must be 16-byte aligned");
+  if (a->rows == 0) return TVT_OK;
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  const long long items = a->rows * (a->d_out / 4);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->out_dtype == TVT_F32)
+    misc::feature_augment_kernel<float><<<misc::grid1d(items, 256), 256, 0, s>>>(a->x, (float*)a->y, a->rows, (int)a->d_in, (int)a->d_out, a->p_drop, a->p_noise, a->noise_std, a->seed);
+  else
+    misc::feature_augment_kernel<__nv_bfloat16><<<misc::grid1d(items, 256), 256, 0, s>>>(a->x, (__nv_bfloat16*)a->y, a->rows, (int)a->d_in, (int)a->d_out, a->p_drop, a->p_noise, a->noise_std, a->seed);
+  return check_launch("tvt_feature_augment");
+}

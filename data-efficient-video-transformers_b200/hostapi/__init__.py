@@ -7,4 +7,5 @@ from .TPN import Reasoning, sum_group, SpatialPyramid  # noqa: F401
 from .fusion import CrossModalBlock, ExpertStream, FusionTransformer, DistillationTrainer  # noqa: F401
 from .inference import EvalBuffer, GraphedForward, REFERENCE_THRESHOLDS  # noqa: F401
 from .collabgating import CollaborativeGating  # noqa: F401
+from .loader import FeatureAugment  # noqa: F401
 from . import vit  # noqa: F401,E402

@@ -417,3 +417,18 @@ def eval_readout(logits, target, probs, labels, pred_bits, top1, row_offset, thr
     a.num_thresholds = len(thresholds)
     a.target_dtype = capi.TVT_F64 if (target is not None and target.dtype == torch.float64) else TVT_F32
     capi.call("tvt_eval_readout", a, _stream())
+
+
+def feature_augment(x, d_out=None, *, p_drop=0.0, p_noise=0.0, noise_std=0.1 ** 0.5, seed=0, out_dtype=torch.bfloat16):
+    """Loader-side pad + train-time feature drop / Gaussian noise + cast in one pass (tvt_feature_augment; reference:
+    src/dataloaders/MMX_Temporal_dl.py:167-181).  x [..., d_in] fp32 -> [..., d_out] out_dtype."""
+    _cuda(x)
+    if x.dtype != torch.float32:
+        raise ValueError("feature_augment: x must be float32 (the loader's dtype)")
+    x = x.contiguous()
+    d_in = x.shape[-1]
+    d_out = d_in if d_out is None else int(d_out)
+    y = torch.empty(*x.shape[:-1], d_out, dtype=out_dtype, device=x.device)
+    a = capi.FeatureAugmentArgs(_p(x), _p(y), x.numel() // d_in, d_in, d_out, p_drop, p_noise, noise_std, seed, _dt(y))
+    capi.call("tvt_feature_augment", a, _stream())
+    return y

@@ -405,6 +405,23 @@ typedef struct {
 } tvt_cls_sum_args;
 TVT_API int tvt_cls_sum_fwd(const tvt_cls_sum_args* args, void* stream);
 
+/* Loader-side feature path on the GPU (src/dataloaders/MMX_Temporal_dl.py:167-181), one pass per expert tensor:
+ *   zero-pad each [1, D_in] feature vector to D_out columns (ConstantPad1d to 2048, :167-169; d_out == d_in skips it),
+ *   train-time add_transforms (:176-181): with probability p_drop the vector becomes zeros, then with probability
+ *   p_noise Gaussian noise N(0, noise_std^2) is added to ALL d_out columns (the padded ones too, as in the reference),
+ *   and the result is written in the activation dtype (fusing the fp32 -> bf16 cast of the embed prologue).
+ * Randomness is counter-based (same hash as dropout): row decisions from hash(seed, row) words, element noise by
+ * Box-Muller on hash(seed ^ stream, row * d_out / 2 + j), so the oracle reproduces every decision bit for bit. */
+typedef struct {
+  const float* x;        /* [rows, d_in] */
+  void* y;               /* [rows, d_out], out_dtype */
+  int64_t rows, d_in, d_out;   /* d_in <= d_out, both multiples of 4 */
+  float p_drop, p_noise, noise_std;   /* 0.3, 0.3, sqrt(0.1) in the reference; both p = 0 at evaluation time */
+  uint64_t seed;
+  int32_t out_dtype;
+} tvt_feature_augment_args;
+TVT_API int tvt_feature_augment(const tvt_feature_augment_args* args, void* stream);
+
 /* Evaluation read-out (src/models/transformer.py:146-158 validation_step + src/callbacks/callbacks.py:34-45): one pass
  * over a batch of logits that appends, at row `row_offset` of caller-owned running buffers of `capacity` rows,
  *   probs = sigmoid(logits)            (what the reference appends to running_logits),

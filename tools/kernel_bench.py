@@ -69,6 +69,13 @@ out = torch.zeros(ff, device=dev)
 ms = timeit(lambda i: ops.colsum(hs[i % 2], out))
 report("colsum [33024,3072] bf16", ms, bytes_=n * ff * 2.0)
 
+# ---- loader-side pad / drop / noise / cast (C5 teacher inputs: 256 clips x 128 frames per expert)
+for D, Dout in ((2048, 2048), (1024, 1024), (128, 2048)):
+    xr = [torch.randn(B * 128, D, device=dev, generator=g) for _ in range(R)]
+    ms = timeit(lambda i: ops.feature_augment(xr[i % R], Dout, p_drop=0.3, p_noise=0.3, seed=5 + i))
+    report(f"feature_augment [{B * 128},{D}]->{Dout} f32->bf16", ms, bytes_=B * 128 * (D * 4.0 + Dout * 2.0))
+del xr
+
 # ---- GEMMs of one encoder layer (forward, dgrad, wgrad)
 mode = ops.Mode("bf16")
 def gemm_case(name, M, N, K, **kw):
