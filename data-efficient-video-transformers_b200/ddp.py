@@ -8,12 +8,31 @@ wgrad kernels' outputs are accumulated by autograd straight into the communicati
 filled in reverse registration order (the order backward produces gradients).  Works with any
 torch.distributed backend (NCCL on GPUs; gloo in the CPU tests of the bucketing logic).
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 
+# id(parameter) -> (weakref to the parameter, weakref to its reducer) for reducers created with direct=True
+_DIRECT = {}
+
+
+def direct_target(p):
+    """If ``p``'s gradient is a view into a bucket of a live ``GradBucketReducer(direct=True)``: ``(grad view, done)``,
+    where a backward kernel may ACCUMULATE (atomics / +=) straight into ``grad view`` and must call ``done()`` once its
+    launches are issued, instead of handing a temporary to autograd (which would cost a zero-fill, a temporary and an
+    ``add_`` launch per parameter).  Otherwise ``None``."""
+    ent = _DIRECT.get(id(p))
+    if ent is None:
+        return None
+    pr, rr = ent[0](), ent[1]()
+    if pr is not p or rr is None or p.grad is None:
+        return None
+    return p.grad, (lambda: rr._on_grad(p))
+
 
 class GradBucketReducer:
-    def __init__(self, params, bucket_bytes=32 << 20, process_group=None, average=True):
+    def __init__(self, params, bucket_bytes=32 << 20, process_group=None, average=True, direct=True):
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
         self.average = average
@@ -30,6 +49,11 @@ class GradBucketReducer:
         if cur:
             self._make_bucket(cur)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.direct = direct
+        if direct:
+            me = weakref.ref(self)
+            for p in self.params:
+                _DIRECT[id(p)] = (weakref.ref(p), me)
 
     ALIGN = 8   # elements: every view starts 32-byte aligned (16 bytes for the bf16 planes laid out alike)
 
@@ -39,7 +63,7 @@ class GradBucketReducer:
             offsets.append(n)
             n += -(-p.numel() // self.ALIGN) * self.ALIGN
         flat = torch.zeros(n, dtype=torch.float32, device=ps[0].device)
-        b = {"flat": flat, "params": list(ps), "offsets": offsets, "pending": len(ps), "handle": None}
+        b = {"flat": flat, "params": list(ps), "offsets": offsets, "pending": len(ps), "handle": None, "seen": set()}
         for p, off in zip(ps, offsets):
             if p.dtype != torch.float32:
                 raise TypeError("GradBucketReducer expects fp32 master parameters")
@@ -53,9 +77,13 @@ class GradBucketReducer:
             b["flat"].zero_()
             b["pending"] = len(b["params"])
             b["handle"] = None
+            b["seen"].clear()
 
     def _on_grad(self, p):
         b = self._index[id(p)]
+        if id(p) in b["seen"]:          # a second contribution to the same parameter in one backward: counted once
+            return
+        b["seen"].add(id(p))
         b["pending"] -= 1
         if b["pending"] == 0 and self.world > 1:
             # async: NCCL's stream waits on the producer stream, backward keeps going on the compute stream
@@ -75,6 +103,10 @@ class GradBucketReducer:
     def remove(self):
         for h in self._hooks:
             h.remove()
+        for p in self.params:
+            ent = _DIRECT.get(id(p))
+            if ent is not None and ent[1]() is self:
+                del _DIRECT[id(p)]
 
 
 def init_from_env(backend=None):

@@ -18,7 +18,7 @@ import math
 
 import torch
 
-from . import ops
+from . import ops, ddp
 from .capi import ACT_GELU, ACT_NONE, ACT_RELU
 
 _seed_counter = [0]
@@ -32,6 +32,33 @@ def next_seed():
 
 def _zeros(n, dev):
     return torch.zeros(n, dtype=torch.float32, device=dev)
+
+
+class _Sink:
+    """Where a backward writes one parameter's gradient.  When the parameter's ``.grad`` is a view into a live gradient
+    bucket (``ddp.GradBucketReducer(direct=True)``) the kernels accumulate straight into it and autograd receives
+    ``None``; otherwise a zero-filled temporary is handed to autograd as usual."""
+
+    def __init__(self, param, shape, dev):
+        tgt = ddp.direct_target(param) if param is not None else None
+        if tgt is not None and tuple(tgt[0].shape) == tuple(shape):
+            self.buf, self._done, self.direct = tgt[0], tgt[1], True
+        else:
+            self.buf, self._done, self.direct = None, None, False
+            self._shape, self._dev = shape, dev
+
+    def zeros(self):
+        """Accumulation target (zero-filled temporary, or the bucket view that zero_grad() cleared)."""
+        if self.buf is None:
+            self.buf = torch.zeros(self._shape, dtype=torch.float32, device=self._dev)
+        return self.buf
+
+    def result(self):
+        """Call after the launches that write the gradient: what to return to autograd."""
+        if self.direct:
+            self._done()
+            return None
+        return self.buf
 
 
 class LayerCfg:
@@ -80,6 +107,7 @@ class EncoderLayerFn(torch.autograd.Function):
         out, mean2, rstd2 = ops.layernorm_fwd(y2, n2_w, n2_b)
         ctx.cfg, ctx.seeds, ctx.dims = cfg, seeds, (n, d, B, H, hd, Sq, Sk, ff)
         ctx.cross = mem is not None
+        ctx.params = (in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b)   # gradient sinks (leaf parameters)
         ctx.save_for_backward(x, mem, qkv, kv, attn, lse, y1, mean1, rstd1, x1, h, z, y2, mean2, rstd2,
                               in_w, out_w, l1_w, l2_w, n1_w, n2_w)
         return out
@@ -93,36 +121,52 @@ class EncoderLayerFn(torch.autograd.Function):
         n, d, B, H, hd, Sq, Sk, ff = ctx.dims
         dev = x.device
         dout = dout.contiguous()
+        P = ctx.params
+        s_inw, s_inb = _Sink(P[0], (3 * d, d), dev), _Sink(P[1], (3 * d,), dev)
+        s_ow, s_ob = _Sink(P[2], (d, d), dev), _Sink(P[3], (d,), dev)
+        s_l1w, s_l1b = _Sink(P[4], (ff, d), dev), _Sink(P[5], (ff,), dev)
+        s_l2w, s_l2b = _Sink(P[6], (d, ff), dev), _Sink(P[7], (d,), dev)
+        s_n1w, s_n1b, s_n2w, s_n2b = (_Sink(P[i], (d,), dev) for i in (8, 9, 10, 11))
+
+        def wgrad(sink, dyp, xp, M, N, K):
+            if sink.direct:
+                m.wgrad(dyp, xp, M, N, K, out=sink.buf, accumulate=True)
+            else:
+                sink.buf = m.wgrad(dyp, xp, M, N, K)
+
         # ---- LN2 and the feed-forward branch
-        dn2w, dn2b, dl2b = _zeros(d, dev), _zeros(d, dev), _zeros(d, dev)
-        dy2, dz2 = ops.layernorm_bwd(dout, y2, mean2, rstd2, n2_w, dgamma=dn2w, dbeta=dn2b, dbias=dl2b,
+        dy2, dz2 = ops.layernorm_bwd(dout, y2, mean2, rstd2, n2_w, dgamma=s_n2w.zeros(), dbeta=s_n2b.zeros(), dbias=s_l2b.zeros(),
                                      dropout_p=p, seed=seeds[3])
+        dn2w, dn2b, dl2b = s_n2w.result(), s_n2b.result(), s_l2b.result()
         dz2p = m.split(dz2)
-        dl2w = m.wgrad(dz2p, m.split(h), n, d, ff)
+        wgrad(s_l2w, dz2p, m.split(h), n, d, ff)
+        dl2w = s_l2w.result()
         dh = m.dgrad(dz2p, n, d, l2_w, relu_mask=h if cfg.act == ACT_RELU else None,
                      gelu_gate=z if cfg.act == ACT_GELU else None, dropout_p=p, seed=seeds[2])
-        dl1b = _zeros(ff, dev)
-        ops.colsum(dh, dl1b)
+        ops.colsum(dh, s_l1b.zeros())
+        dl1b = s_l1b.result()
         dhp = m.split(dh)
-        dl1w = m.wgrad(dhp, m.split(x1), n, ff, d)
+        wgrad(s_l1w, dhp, m.split(x1), n, ff, d)
+        dl1w = s_l1w.result()
         dx1 = m.dgrad(dhp, n, ff, l1_w, residual=dy2)
         # ---- LN1 and the attention branch
-        dn1w, dn1b, dob = _zeros(d, dev), _zeros(d, dev), _zeros(d, dev)
-        dy1, dz1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, n1_w, dgamma=dn1w, dbeta=dn1b, dbias=dob,
+        dy1, dz1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, n1_w, dgamma=s_n1w.zeros(), dbeta=s_n1b.zeros(), dbias=s_ob.zeros(),
                                      dropout_p=p, seed=seeds[1])
+        dn1w, dn1b, dob = s_n1w.result(), s_n1b.result(), s_ob.result()
         dz1p = m.split(dz1)
-        dow = m.wgrad(dz1p, m.split(attn), n, d, d)
+        wgrad(s_ow, dz1p, m.split(attn), n, d, d)
+        dow = s_ow.result()
         dattn = m.dgrad(dz1p, n, d, out_w)
         scale = 1.0 / math.sqrt(hd)
-        dinb = _zeros(3 * d, dev)
+        dinb_buf = s_inb.zeros()
         if not ctx.cross:
             dqkv = torch.empty_like(qkv)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
             ops.attention_bwd(q, k, v, attn, dattn, lse, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H, Sq, Sk,
                               hd, scale, dropout_p=p, seed=seeds[0], impl=cfg.attn_impl)
-            ops.colsum(dqkv, dinb)
+            ops.colsum(dqkv, dinb_buf)
             dqkvp = m.split(dqkv)
-            dinw = m.wgrad(dqkvp, m.split(x), n, 3 * d, d)
+            wgrad(s_inw, dqkvp, m.split(x), n, 3 * d, d)
             dx = m.dgrad(dqkvp, n, 3 * d, in_w, residual=dy1) if ctx.needs_input_grad[1] else None
             dmem = None
         else:
@@ -131,14 +175,16 @@ class EncoderLayerFn(torch.autograd.Function):
             dkv = torch.empty_like(kv)
             ops.attention_bwd(qkv, kv[:, :d], kv[:, d:], attn, dattn, lse, dq, dkv[:, :d], dkv[:, d:], B, H, Sq, Sk,
                               hd, scale, dropout_p=p, seed=seeds[0], impl=cfg.attn_impl)
-            ops.colsum(dq, dinb[:d])
-            ops.colsum(dkv, dinb[d:])
+            ops.colsum(dq, dinb_buf[:d])
+            ops.colsum(dkv, dinb_buf[d:])
             dqp, dkvp = m.split(dq), m.split(dkv)
-            dinw = torch.empty(3 * d, d, dtype=torch.float32, device=dev)
-            m.wgrad(dqp, m.split(x), n, d, d, out=dinw[:d])
-            m.wgrad(dkvp, m.split(mem), nk, 2 * d, d, out=dinw[d:])
+            if not s_inw.direct:
+                s_inw.buf = torch.empty(3 * d, d, dtype=torch.float32, device=dev)
+            m.wgrad(dqp, m.split(x), n, d, d, out=s_inw.buf[:d], accumulate=s_inw.direct)
+            m.wgrad(dkvp, m.split(mem), nk, 2 * d, d, out=s_inw.buf[d:], accumulate=s_inw.direct)
             dx = m.dgrad(dqp, n, d, in_w, residual=dy1, rows=(0, d)) if ctx.needs_input_grad[1] else None
             dmem = m.dgrad(dkvp, nk, 2 * d, in_w, rows=(d, 3 * d)) if ctx.needs_input_grad[2] else None
+        dinw, dinb = s_inw.result(), s_inb.result()
         return (None, dx, dmem, dinw, dinb, dow, dob, dl1w, dl1b, dl2w, dl2b, dn1w, dn1b, dn2w, dn2b)
 
 
@@ -269,6 +315,7 @@ class LinearFn(torch.autograd.Function):
         xp = mode.split(x)
         y = mode.linear_fwd(xp, M, K, w, b)
         ctx.mode = mode
+        ctx.params = (w, b)
         ctx.save_for_backward(x, w)
         return y
 
@@ -278,12 +325,16 @@ class LinearFn(torch.autograd.Function):
         m = ctx.mode
         M, K = x.shape
         N = w.shape[0]
-        dyp = m.split(dy.contiguous())
-        dw = m.wgrad(dyp, m.split(x), M, N, K)
-        db = _zeros(N, dy.device)
-        ops.colsum(dy, db)
+        dy = dy.contiguous()
+        dyp = m.split(dy)
+        s_w, s_b = _Sink(ctx.params[0], (N, K), dy.device), _Sink(ctx.params[1], (N,), dy.device)
+        if s_w.direct:
+            m.wgrad(dyp, m.split(x), M, N, K, out=s_w.buf, accumulate=True)
+        else:
+            s_w.buf = m.wgrad(dyp, m.split(x), M, N, K)
+        ops.colsum(dy, s_b.zeros())
         dx = m.dgrad(dyp, M, N, w) if ctx.needs_input_grad[1] else None
-        return None, dx, dw, db
+        return None, dx, s_w.result(), s_b.result()
 
 
 class MlpFn(torch.autograd.Function):
@@ -324,6 +375,7 @@ class MlpFn(torch.autograd.Function):
             cur = y
         ctx.mode, ctx.acts, ctx.drops, ctx.seeds, ctx.nl = mode, acts, drops, seeds, nl
         ctx.save_for_backward(x, *ys, *[z if z is not None else x.new_empty(0) for z in zs], *ws)
+        ctx.params = (ws, bs)
         return cur
 
     @staticmethod
@@ -345,9 +397,13 @@ class MlpFn(torch.autograd.Function):
             inp = ys[i - 1] if i > 0 else x
             N, K = ws[i].shape
             dprep = m.split(dpre)
-            dws[i] = m.wgrad(dprep, m.split(inp), M, N, K)
-            dbs[i] = _zeros(N, dy.device)
-            ops.colsum(dpre, dbs[i])
+            s_w, s_b = _Sink(ctx.params[0][i], (N, K), dy.device), _Sink(ctx.params[1][i], (N,), dy.device)
+            if s_w.direct:
+                m.wgrad(dprep, m.split(inp), M, N, K, out=s_w.buf, accumulate=True)
+            else:
+                s_w.buf = m.wgrad(dprep, m.split(inp), M, N, K)
+            ops.colsum(dpre, s_b.zeros())
+            dws[i], dbs[i] = s_w.result(), s_b.result()
             if i > 0:
                 dpre = m.dgrad(dprep, M, N, ws[i], relu_mask=ys[i - 1] if acts[i - 1] == ACT_RELU else None,
                                gelu_gate=zs[i - 1] if acts[i - 1] == ACT_GELU else None,

@@ -199,14 +199,15 @@ class Mode:
         return dx
 
     # dW[N,K] = dy[M,N]^T x[M,K]  (fp32, split-K over the token dimension when the tile grid is small)
-    def wgrad(self, dyp, xp, M, N, K, out=None):
+    def wgrad(self, dyp, xp, M, N, K, out=None, accumulate=False):
+        """dW[N, K] = dY^T X.  ``accumulate=True`` adds into ``out`` (fp32 atomics) instead of overwriting it."""
         splits = pick_splits(((N + 127) // 128) * ((K + 255) // 256), (M + 63) // 64)
         if out is None:
             out = (torch.zeros if splits > 1 else torch.empty)(N, K, dtype=torch.float32, device=dyp[0].device)
-        elif splits > 1:
+        elif splits > 1 and not accumulate:
             out.zero_()
         gemm(dyp[0], xp[0], N, K, M, a_lo=dyp[1], b_lo=xp[1], a_mn=True, b_mn=True, lda=_rowmajor(dyp[0]),
-             ldb=_rowmajor(xp[0]), out_f32=out, splits=splits, atomic=splits > 1)
+             ldb=_rowmajor(xp[0]), out_f32=out, splits=splits, atomic=splits > 1 or accumulate)
         return out
 
 

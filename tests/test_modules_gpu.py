@@ -487,3 +487,40 @@ def test_collaborative_gating_parity(api, precision):
         assert torch.equal(mod(nested), mod(xs))
     yard = _yardstick(ref, precision, lambda m: (_ac(lambda: m(xs)).float() * w).sum())
     grads_close(mod, ref, TOL[precision], "collab ", yard=yard)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_direct_gradient_sinks_match_autograd_accumulation(api, precision):
+    """With a GradBucketReducer(direct=True) the backward kernels accumulate straight into the flat gradient buckets
+    (no temporaries, zero-fills or add_ launches): same gradients as autograd's accumulation, every bucket's
+    all-reduce trigger still fires, and a second backward without zero_grad accumulates (torch semantics)."""
+    from tvt_b200 import ddp
+    kw = dict(in_dims=(64, 32), d=64, nhead=2, nhid=128, nlayers=2, dropout=0.0, batch_size=8, frames=12, n_classes=15,
+              fusion="cross", pyramid=True, precision=precision)
+    gen = torch.Generator().manual_seed(5)
+    xs = [torch.randn(8, 12, D, generator=gen).to(DEV) for D in (64, 32)]
+    y = _targets(8, 15, gen).to(DEV)
+    grads = {}
+    for direct in (False, True):
+        torch.manual_seed(1130)
+        mod = _no_dropout(api.FusionTransformer(**kw)).to(DEV).train()
+        red = ddp.GradBucketReducer(list(mod.parameters()), bucket_bytes=1 << 16, direct=direct)
+        assert len(red.buckets) >= 2
+        red.zero_grad()
+        logits, _, ploss = mod(xs, y)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y) + ploss[0]
+        loss.backward()
+        used = [b for b in red.buckets if any(id(p) in b["seen"] for p in b["params"])]
+        assert all(b["pending"] == len(b["params"]) - len(b["seen"]) for b in red.buckets)
+        assert sum(len(b["seen"]) for b in red.buckets) >= 0.8 * len(red.params) and used
+        red.finish()
+        grads[direct] = {n: p.grad.clone() for n, p in mod.named_parameters()}
+        if direct:
+            logits, _, ploss = mod(xs, y)                      # second backward, no zero_grad: accumulates
+            (torch.nn.functional.binary_cross_entropy_with_logits(logits, y) + ploss[0]).backward()
+            for n, p in mod.named_parameters():
+                assert_close(p.grad, 2 * grads[True][n], 1e-5 if precision == "fp32" else 1e-3, "accumulated " + n)
+        red.remove()
+    for n in grads[False]:
+        assert_close(grads[True][n], grads[False][n], 1e-6, "direct " + n)
+    assert ddp.direct_target(next(mod.parameters())) is None   # removed reducers no longer capture gradients
