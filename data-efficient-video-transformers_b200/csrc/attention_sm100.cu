@@ -1152,6 +1152,376 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------- backward, v3
+// Single key chunk (Sk <= 144) and Sq <= 128 + kMaxTail: every self-attention of the model family.  Same tiles, TMEM
+// columns and tail-row scheme as bwd2_kernel, re-scheduled after a phase-stamp profile of that kernel (tools/attn_stamps.py:
+// 31 k clk per CTA, of which D-from-global 4.4 k, K/V TMA issue 2.3 k, P/dS pass 8.2 k, unrolled MMA issue 3.7 k, drains
+// 5.7 k, the one-key tail pass 3.9 k):
+//   * Q, dO, O, K, V all arrive by TMA issued at t = 0 (one box each; O lands in the not-yet-used P block 0 and
+//     D_i = sum_c dO_ic O_ic is computed from shared memory);
+//   * four tail-row warps split the keys (warp 8's lane 0 is also the TMA / MMA issuer);
+//   * lean P / dS arithmetic: ex2.approx, masking only as a bitwise fix-up of the last (partial) block, softmax scale
+//     applied when dK / dQ leave instead of per dS element;
+//   * dV / dK of the tail keys are issued with the main gradient MMAs into the (by then free) S columns, so there is no
+//     second sync / commit / drain round; two commits let the dK / dV drains overlap the dQ and tail-key MMAs;
+//   * rolled issue loops and ONE out-of-line drain routine: the kernel is straight-line code executed once per CTA, so
+//     its instruction footprint is fetch time.
+// TMEM: S [0,144) | dP [160,304) | dK [320,384) | dV [384,448) | dQ [448,512); tail keys: dV_t [0,64) | dK_t [64,128)
+// smem: Q 16K | dO 16K | P 48K (block 0 first holds O) | dS 48K | K 18K | V 18K | barriers | D partials | tail scratch
+constexpr int kThreadsBwd3 = 384;   // warps 0-7 workers (two threads per row), warps 8-11 tail query rows
+
+#ifdef TVT_ATTN_STAMPS
+__device__ long long g_stamps[3][32];
+#define TVT_STAMP(slot)                                                                                                  \
+  do {                                                                                                                   \
+    const int sb_ = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : (blockIdx.x == gridDim.x - 1 ? 2 : -1));    \
+    if (sb_ >= 0) g_stamps[sb_][slot] = clock64();                                                                       \
+  } while (0)
+#else
+#define TVT_STAMP(slot) do {} while (0)
+#endif
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
+// Rows of a [128 x 32 * pieces] fp32 accumulator -> bf16 global rows (thread == row): out = (acc + sum_t w_t * vec_t) * mul,
+// the rank-1 terms being the tail query rows' contributions (w_t = per-row weight at w_s + t * KC floats, vec_t = 64-float
+// vector at vec_s + t * HD floats).  Deliberately not inlined: one copy serves dK, dV, their tail keys and dQ.
+__device__ __noinline__ void drain_rows(uint32_t taddr, __nv_bfloat16* dst, bool ok, int pieces, float mul, int ntail, uint32_t w_s,
+                                        uint32_t vec_s) {
+#pragma unroll 1
+  for (int pc = 0; pc < pieces; ++pc) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + 32 * pc, r);
+    tmem_ld_wait_dep(r);
+    if (ok) {
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+#pragma unroll 1
+      for (int t = 0; t < ntail; ++t) {
+        const float wj = lds_f32(w_s + t * KC * 4);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const uint4 v = lds128(vec_s + (t * HD + 32 * pc + i) * 4);
+          f[i] += wj * __uint_as_float(v.x);
+          f[i + 1] += wj * __uint_as_float(v.y);
+          f[i + 2] += wj * __uint_as_float(v.z);
+          f[i + 3] += wj * __uint_as_float(v.w);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(dst + 32 * pc + 8 * g) =
+            make_uint4(pack_bf16x2(f[8 * g] * mul, f[8 * g + 1] * mul), pack_bf16x2(f[8 * g + 2] * mul, f[8 * g + 3] * mul),
+                       pack_bf16x2(f[8 * g + 4] * mul, f[8 * g + 5] * mul), pack_bf16x2(f[8 * g + 6] * mul, f[8 * g + 7] * mul));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                                                            const __grid_constant__ CUtensorMap tmO, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + 16384;
+  uint8_t* sP = sdO + 16384;        // 3 k-blocks; block 0 holds the O tile until D has been computed
+  uint8_t* sdS = sP + 3 * 16384;    // 3 k-blocks; the MN-major tail-key operand runs 16 KB past block 2 into sK (finite data, rows never drained)
+  uint8_t* sK = sdS + 3 * 16384;
+  uint8_t* sV = sK + KC * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KC * 128);
+  uint64_t* bar_ld = bars;          // Q, dO, O, K, V landed
+  uint64_t* bar_s = bars + 1;       // S and dP complete
+  uint64_t* bar_g1 = bars + 2;      // dV, dK (keys 0..127) complete
+  uint64_t* bar_g2 = bars + 3;      // dQ and the tail keys' dV, dK complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* sDh = reinterpret_cast<float*>(bars + 8);  // [2][128] per-half partial D
+  float* tq = sDh + 256;                            // [kMaxTail][64] tail query rows
+  float* tdo = tq + kMaxTail * HD;                  // [kMaxTail][64] tail dO rows
+  float* tdq = tdo + kMaxTail * HD;                 // [kMaxTail][64] tail dQ accumulators (shared atomics of the four tail warps)
+  float* tp = tdq + kMaxTail * HD;                  // [kMaxTail][KC] P * mask of the tail rows
+  float* tds = tp + kMaxTail * KC;                  // [kMaxTail][KC] dS / scale of the tail rows
+  float* tDL = tds + kMaxTail * KC;                 // [kMaxTail][2]  D_t, lse_t * log2e
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool worker = warp < 8;
+  const int row = tid & 127, half = (tid >> 7) & 1;   // two worker threads per row: they split the columns
+  const bool issuer = warp == 8 && lane == 0;
+  const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
+  const int n_main = p.Sq < 128 ? p.Sq : 128;       // valid rows of the tensor-core tile
+  const int ntail = p.Sq - n_main;                  // rows handled by the tail warps
+  const int nk = p.sk_pad;                          // padded keys (multiple of 16, <= KC)
+  if (tid == 0) TVT_STAMP(0);
+  if (issuer) {
+    mbar_init(smem_u32(bar_ld), 1);
+    mbar_init(smem_u32(bar_s), 1);
+    mbar_init(smem_u32(bar_g1), 1);
+    mbar_init(smem_u32(bar_g2), 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(smem_u32(bar_ld), 3 * 16384 + 2 * nk * 128);
+    tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_ld), h * HD, b * p.Sq);
+    tma_load_2d(smem_u32(sK), &tmK, smem_u32(bar_ld), h * HD, b * p.Sk);
+    tma_load_2d(smem_u32(sdO), &tmdO, smem_u32(bar_ld), h * HD, b * p.Sq);
+    tma_load_2d(smem_u32(sV), &tmV, smem_u32(bar_ld), h * HD, b * p.Sk);
+    tma_load_2d(smem_u32(sP), &tmO, smem_u32(bar_ld), h * HD, b * p.Sq);
+  }
+  if (warp == 8) {
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  float Li = 0.0f;
+  if (worker) {
+    if (row < n_main) Li = p.lse[static_cast<long long>(bh) * p.Sq + row] * kLog2e;
+  } else if (warp == 9) {
+    for (int t = 0; t < ntail; ++t) {
+      const long long grow = static_cast<long long>(b) * p.Sq + n_main + t;
+      const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.q_in + grow * p.ldq + h * HD + 2 * lane));
+      const float2 d2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.do_in + grow * p.lddo + h * HD + 2 * lane));
+      const float2 o2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.o_in + grow * p.ldo + h * HD + 2 * lane));
+      tq[t * HD + 2 * lane] = q2.x; tq[t * HD + 2 * lane + 1] = q2.y;
+      tdo[t * HD + 2 * lane] = d2.x; tdo[t * HD + 2 * lane + 1] = d2.y;
+      tdq[t * HD + 2 * lane] = 0.0f; tdq[t * HD + 2 * lane + 1] = 0.0f;
+      const float Dt = warp_sum(d2.x * o2.x + d2.y * o2.y);
+      if (lane == 0) {
+        tDL[2 * t] = Dt;
+        tDL[2 * t + 1] = p.lse[static_cast<long long>(bh) * p.Sq + n_main + t] * kLog2e;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();                  // #1: TMEM base address and tail scratch visible
+  tc_fence_after();
+  if (tid == 0) TVT_STAMP(1);
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 160, tdK = tmem_base + 320, tdV = tmem_base + 384, tdQ = tmem_base + 448;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const float sl2 = p.scale * kLog2e;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(bar_ld), 0);
+      TVT_STAMP(16);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, nk, false, false);
+#pragma unroll 1
+      for (int k = 0; k < HD / 16; ++k) {
+        tc_mma_f16_ss(tS, make_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024), make_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc, k > 0);
+        tc_mma_f16_ss(tdP, make_smem_desc_sw128(smem_u32(sdO) + k * 32, 16, 1024), make_smem_desc_sw128(smem_u32(sV) + k * 32, 16, 1024), idesc, k > 0);
+      }
+      tc_commit(smem_u32(bar_s));
+      TVT_STAMP(17);
+    }
+    __syncwarp();
+  }
+  if (worker) {
+    // D_i = sum_c dO_ic O_ic from the shared-memory tiles (each half sums 32 of the 64 columns)
+    mbar_wait(smem_u32(bar_ld), 0);
+    float acc = 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      float a[8], d[8];
+      Vec16<__nv_bfloat16>::unpack(lds128(smem_u32(sP) + sw128(row, 4 * half + ch)), a);
+      Vec16<__nv_bfloat16>::unpack(lds128(smem_u32(sdO) + sw128(row, 4 * half + ch)), d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc += a[i] * d[i];
+    }
+    sDh[half * 128 + row] = acc;
+  }
+  __syncthreads();                  // #2: D partials visible; O has been read, P block 0 may be overwritten
+  if (tid == 0) TVT_STAMP(2);
+
+  if (worker) {
+    mbar_wait(smem_u32(bar_s), 0);
+    tc_fence_after();
+    if (tid == 0) TVT_STAMP(3);
+    const bool row_ok = row < n_main;
+    const int lim = row_ok ? p.Sk : 0;          // valid keys of this row: query rows beyond the sequence must come out as zeros
+    const float Di = sDh[row] + sDh[128 + row];
+    const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? row : 0);
+#pragma unroll 1
+    for (int c0 = 16 * half; c0 < nk; c0 += 32) {   // the two halves interleave 16-column blocks
+      uint32_t rs[16], rp[16];
+      tmem_ld_32x32b_x16(tS + lane_addr + c0, rs);
+      tmem_ld_32x32b_x16(tdP + lane_addr + c0, rp);
+      float m[16];
+      if (p.dropout_thr16) {
+        drop_mul16(p, rowkey, c0, m);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m[i] = 1.0f;
+      }
+      tmem_ld_wait_dep(rs, rp);
+      uint32_t pp[8], pd[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(rs[i]), sl2, -Li));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(rs[i + 1]), sl2, -Li));
+        const float d0 = p0 * fmaf(__uint_as_float(rp[i]), m[i], -Di);
+        const float d1 = p1 * fmaf(__uint_as_float(rp[i + 1]), m[i + 1], -Di);
+        pp[i >> 1] = pack_bf16x2(p0 * m[i], p1 * m[i + 1]);
+        pd[i >> 1] = pack_bf16x2(d0, d1);
+      }
+      if (c0 + 16 > lim) {          // partial block (padding keys hold other rows' data) or a row beyond the sequence
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const int c = c0 + 2 * w;
+          const uint32_t keep = c + 1 < lim ? 0xFFFFFFFFu : (c < lim ? 0x0000FFFFu : 0u);
+          pp[w] &= keep;
+          pd[w] &= keep;
+        }
+      }
+      const uint32_t blk = (c0 >> 6) * 16384;
+      const int ch = (c0 & 63) >> 3;
+      sts128(smem_u32(sP) + blk + sw128(row, ch), pp[0], pp[1], pp[2], pp[3]);
+      sts128(smem_u32(sP) + blk + sw128(row, ch + 1), pp[4], pp[5], pp[6], pp[7]);
+      sts128(smem_u32(sdS) + blk + sw128(row, ch), pd[0], pd[1], pd[2], pd[3]);
+      sts128(smem_u32(sdS) + blk + sw128(row, ch + 1), pd[4], pd[5], pd[6], pd[7]);
+    }
+    fence_proxy_async_smem();
+    if (tid == 0) TVT_STAMP(4);
+  } else if (ntail > 0) {
+    // tail query rows on CUDA cores: tail warp tw takes keys [32 tw, 32 tw + 32) and, beyond 128, [128 + 32 tw, ...)
+    const int tw = warp - 8;
+    mbar_wait(smem_u32(bar_ld), 0);
+    if (lane == 0) TVT_STAMP(24 + tw);
+    for (int t = 0; t < ntail; ++t) {
+      const float Dt = tDL[2 * t], Lt = tDL[2 * t + 1];
+      const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, n_main + t);
+      float a0 = 0.0f, a1 = 0.0f;
+      for (int jb = 32 * tw; jb < nk; jb += 128) {
+        const int j = jb + lane;
+        if (j < nk) {
+          float pm = 0.0f, dsv = 0.0f;
+          if (j < p.Sk) {
+            float sacc = 0.0f, dacc = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+              float kf[8], vf[8];
+              Vec16<__nv_bfloat16>::unpack(lds128(smem_u32(sK) + sw128(j, c)), kf);
+              Vec16<__nv_bfloat16>::unpack(lds128(smem_u32(sV) + sw128(j, c)), vf);
+#pragma unroll
+              for (int i = 0; i < 8; i += 4) {
+                const uint4 q4 = lds128(smem_u32(tq) + (t * HD + c * 8 + i) * 4);
+                const uint4 o4 = lds128(smem_u32(tdo) + (t * HD + c * 8 + i) * 4);
+                sacc += __uint_as_float(q4.x) * kf[i] + __uint_as_float(q4.y) * kf[i + 1] + __uint_as_float(q4.z) * kf[i + 2] + __uint_as_float(q4.w) * kf[i + 3];
+                dacc += __uint_as_float(o4.x) * vf[i] + __uint_as_float(o4.y) * vf[i + 1] + __uint_as_float(o4.z) * vf[i + 2] + __uint_as_float(o4.w) * vf[i + 3];
+              }
+            }
+            float m = 1.0f;
+            if (p.dropout_thr16) {
+              const uint64_t bits = attn_drop_bits(p.dropout_seed, rowkey, j >> 2);
+              m = dropout_keep_lane(bits, j & 3, p.dropout_thr16) ? p.dropout_scale : 0.0f;
+            }
+            const float prob = ex2_approx(fmaf(sacc, sl2, -Lt));
+            dsv = prob * (dacc * m - Dt);
+            pm = prob * m;
+          }
+          tp[t * KC + j] = pm;
+          tds[t * KC + j] = dsv;
+        }
+        __syncwarp();
+        const int jn = nk - jb < 32 ? nk - jb : 32;
+#pragma unroll 4
+        for (int jj = 0; jj < jn; ++jj) {
+          const float dsj = tds[t * KC + jb + jj];
+          const float2 k2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sw_elem(sK, jb + jj, 2 * lane)));
+          a0 += dsj * k2.x;
+          a1 += dsj * k2.y;
+        }
+      }
+      atomicAdd(&tdq[t * HD + 2 * lane], a0);
+      atomicAdd(&tdq[t * HD + 2 * lane + 1], a1);
+    }
+    if (lane == 0) TVT_STAMP(28 + tw);
+  }
+  tc_fence_before();
+  __syncthreads();                  // #3: P, dS tiles and the tail rows' p / ds vectors complete; S / dP columns free
+  if (tid == 0) TVT_STAMP(5);
+  if (issuer) {
+    tc_fence_after();
+    // dV = P^T dO, dK = dS^T Q for keys 0..127: A MN-major (two 64-key blocks, LBO 16 KB), contraction over queries
+    const uint32_t idesc_mn = make_idesc_bf16(128, HD, true, true);
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+      tc_mma_f16_ss(tdV, make_smem_desc_sw128(smem_u32(sP) + k * 2048, 16384, 1024), make_smem_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024),
+                    idesc_mn, k > 0);
+      tc_mma_f16_ss(tdK, make_smem_desc_sw128(smem_u32(sdS) + k * 2048, 16384, 1024), make_smem_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024),
+                    idesc_mn, k > 0);
+    }
+    tc_commit(smem_u32(bar_g1));
+    TVT_STAMP(18);
+    // dQ = dS K: contraction over the nk keys
+    const uint32_t idesc_q = make_idesc_bf16(128, HD, false, true);
+#pragma unroll 1
+    for (int k = 0; k < nk / 16; ++k)
+      tc_mma_f16_ss(tdQ, make_smem_desc_sw128(smem_u32(sdS + (k >> 2) * 16384) + (k & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_q, k > 0);
+    if (nk > 128) {
+      // tail keys 128..nk-1 from the third k-block, into the S columns: dV_t [0,64) | dK_t [64,128)
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k) {
+        tc_mma_f16_ss(tS, make_smem_desc_sw128(smem_u32(sP) + 2 * 16384 + k * 2048, 16384, 1024),
+                      make_smem_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024), idesc_mn, k > 0);
+        tc_mma_f16_ss(tS + 64, make_smem_desc_sw128(smem_u32(sdS) + 2 * 16384 + k * 2048, 16384, 1024),
+                      make_smem_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024), idesc_mn, k > 0);
+      }
+    }
+    tc_commit(smem_u32(bar_g2));
+    TVT_STAMP(19);
+  }
+  if (worker) {
+    // half 0 drains dK (+ ds_t q_t, x scale), half 1 drains dV (+ p_t dO_t); thread == key row
+    __nv_bfloat16* gbase = half ? p.dv : p.dk;
+    const long long gld = half ? p.lddv : p.lddk;
+    const uint32_t w_s = smem_u32(half ? tp : tds), vec_s = smem_u32(half ? tdo : tq);
+    const float mul = half ? 1.0f : p.scale;
+    mbar_wait(smem_u32(bar_g1), 0);
+    tc_fence_after();
+    if (tid == 0) TVT_STAMP(6);
+    if ((warp & 3) * 32 < p.Sk) {
+      const bool ok = row < p.Sk;
+      drain_rows((half ? tdV : tdK) + lane_addr, gbase + (static_cast<long long>(b) * p.Sk + (ok ? row : 0)) * gld + h * HD, ok, 2, mul, ntail,
+                 w_s + row * 4, vec_s);
+    }
+    if (tid == 0) TVT_STAMP(7);
+    mbar_wait(smem_u32(bar_g2), 0);
+    tc_fence_after();
+    if (tid == 0) TVT_STAMP(8);
+    if (nk > 128 && (warp & 3) == 0) {            // tail keys: lanes of the first TMEM quadrant
+      const int key = 128 + row;
+      const bool ok = key < p.Sk;
+      drain_rows(tS + (half ? 0 : 64) + lane_addr, gbase + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * gld + h * HD, ok, 2, mul, ntail,
+                 w_s + (ok ? key : 0) * 4, vec_s);
+    }
+    if ((warp & 3) * 32 < n_main) {               // dQ of the main rows: each half takes 32 columns
+      const bool ok = row < n_main;
+      drain_rows(tdQ + 32 * half + lane_addr, p.dq + (static_cast<long long>(b) * p.Sq + (ok ? row : 0)) * p.lddq + h * HD + 32 * half, ok, 1,
+                 p.scale, 0, 0, 0);
+    }
+    if (tid == 0) TVT_STAMP(9);
+  } else if (warp == 9) {
+    for (int t = 0; t < ntail; ++t) {
+      __nv_bfloat16* dqrow = p.dq + (static_cast<long long>(b) * p.Sq + n_main + t) * p.lddq + h * HD;
+      *reinterpret_cast<__nv_bfloat162*>(dqrow + 2 * lane) =
+          __floats2bfloat162_rn(tdq[t * HD + 2 * lane] * p.scale, tdq[t * HD + 2 * lane + 1] * p.scale);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) TVT_STAMP(10);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1260,6 +1630,19 @@ int launch_bwd(const tvt_attention_bwd_args* a, cudaStream_t s) {
   if ((rc = make_map(&tk, a->k, a->batch * a->sk, w, a->ldk)) != TVT_OK) return rc;
   if ((rc = make_map(&tv, a->v, a->batch * a->sk, w, a->ldv)) != TVT_OK) return rc;
   if ((rc = make_map(&tdo, a->d_o, a->batch * a->sq, w, a->lddo)) != TVT_OK) return rc;
+  if (p.Sq <= 128 + kMaxTail && p.sk_pad <= KC) {
+    CUtensorMap tq128, tdo128, to128, tk1, tv1;     // one box per operand
+    if ((rc = make_map(&tq128, a->q, a->batch * a->sq, w, a->ldq, 128)) != TVT_OK) return rc;
+    if ((rc = make_map(&tdo128, a->d_o, a->batch * a->sq, w, a->lddo, 128)) != TVT_OK) return rc;
+    if ((rc = make_map(&to128, a->o, a->batch * a->sq, w, a->ldo, 128)) != TVT_OK) return rc;
+    if ((rc = make_map(&tk1, a->k, a->batch * a->sk, w, a->ldk, p.sk_pad)) != TVT_OK) return rc;
+    if ((rc = make_map(&tv1, a->v, a->batch * a->sk, w, a->ldv, p.sk_pad)) != TVT_OK) return rc;
+    p.q_in = (const __nv_bfloat16*)a->q; p.ldq = a->ldq;
+    const size_t bytes3 = 1024 + 2 * 16384 + 6 * 16384 + 2 * (size_t)KC * 128 + 64 + 256 * 4 + (3 * kMaxTail * HD + 2 * kMaxTail * KC + 2 * kMaxTail) * 4;
+    if ((rc = set_smem(bwd3_kernel, bytes3, "tvt_attention_bwd")) != TVT_OK) return rc;
+    bwd3_kernel<<<p.B * p.H, kThreadsBwd3, bytes3, s>>>(tq128, tk1, tv1, tdo128, to128, p);
+    return check_launch("tvt_attention_bwd");
+  }
   if (p.Sq <= 128 + kMaxTail) {
     CUtensorMap tq128, tdo128;
     if ((rc = make_map(&tq128, a->q, a->batch * a->sq, w, a->ldq, 128)) != TVT_OK) return rc;
@@ -1279,3 +1662,9 @@ int launch_bwd(const tvt_attention_bwd_args* a, cudaStream_t s) {
 
 }  // namespace attn_tc
 }  // namespace tvt
+
+#ifdef TVT_ATTN_STAMPS
+extern "C" __attribute__((visibility("default"))) int tvt_debug_attn_stamps(long long* out) {
+  return cudaMemcpyFromSymbol(out, tvt::attn_tc::g_stamps, sizeof(long long) * 3 * 32) == cudaSuccess ? 0 : -1;
+}
+#endif

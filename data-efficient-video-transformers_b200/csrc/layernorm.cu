@@ -78,11 +78,15 @@ __global__ void __launch_bounds__(kWarps * 32, kChunks <= 4 ? 3 : 1) ln_fwd_kern
         if (pe_row) {
 #pragma unroll
           for (int i = 0; i < V; ++i) v[c][i] += pe_row[col + i];
-          if (p.dropout_thr16) {
+          if (p.dropout_thr16) {   // d % 8 == 0: the row's element index is a multiple of 4, so one hash serves 4 elements
+            const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.d + col) >> 2;
 #pragma unroll
-            for (int i = 0; i < V; ++i)
-              v[c][i] = dropout_keep(p.dropout_seed, static_cast<unsigned long long>(row) * p.d + col + i, p.dropout_thr16)
-                            ? v[c][i] * p.dropout_scale : 0.0f;
+            for (int g = 0; g < V / 4; ++g) {
+              const uint64_t bits = dropout_bits4(p.dropout_seed, e4 + g);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                v[c][4 * g + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? v[c][4 * g + i] * p.dropout_scale : 0.0f;
+            }
           }
           if (p.pre) Vec16<T>::store(reinterpret_cast<T*>(p.pre) + row * p.d + col, v[c]);
         }
@@ -242,11 +246,15 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kChunks <= 4 ? 3 : 1) ln_bwd_k
           for (int i = 0; i < V; ++i) o[i] += rr[i];
         }
         if (dx_row) Vec16<T>::store(dx_row + col, o);
-        if (p.dropout_thr16) {
+        if (p.dropout_thr16) {   // dropout_ld % 4 == 0 and col % 4 == 0: one hash per 4 consecutive elements
+          const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.dropout_ld + col) >> 2;
 #pragma unroll
-          for (int i = 0; i < V; ++i)
-            o[i] = dropout_keep(p.dropout_seed, static_cast<unsigned long long>(row) * p.dropout_ld + col + i, p.dropout_thr16)
-                       ? o[i] * p.dropout_scale : 0.0f;
+          for (int g = 0; g < V / 4; ++g) {
+            const uint64_t bits = dropout_bits4(p.dropout_seed, e4 + g);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o[4 * g + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? o[4 * g + i] * p.dropout_scale : 0.0f;
+          }
         }
         if (dz_row) Vec16<T>::store(dz_row + col, o);
 #pragma unroll

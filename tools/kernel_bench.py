@@ -64,6 +64,10 @@ y, mean, rstd = ops.layernorm_fwd(xs[0], gamma, beta)
 dg, db, dbias = (torch.zeros(d, device=dev) for _ in range(3))
 ms = timeit(lambda i: ops.layernorm_bwd(xs[(i + 1) % R], xs[i % R], mean, rstd, gamma, dgamma=dg, dbeta=db, dbias=dbias))
 report("layernorm_bwd [33024,768] bf16", ms, bytes_=3.0 * n * d * 2 + 8 * n)
+ms = timeit(lambda i: ops.layernorm_bwd(xs[(i + 1) % R], xs[i % R], mean, rstd, gamma, dgamma=dg, dbeta=db, dbias=dbias, dropout_p=0.5, seed=7))
+report("layernorm_bwd + dropout-masked dz (LN2 of a layer)", ms, bytes_=4.0 * n * d * 2 + 8 * n)
+ms = timeit(lambda i: ops.layernorm_bwd(xs[(i + 1) % R], xs[i % R], mean, rstd, gamma, dgamma=dg, dbeta=db, dres=xs[(i + 2) % R]))
+report("layernorm_bwd + residual-path gradient", ms, bytes_=4.0 * n * d * 2 + 8 * n)
 hs = [bf(n, ff) for _ in range(2)]
 out = torch.zeros(ff, device=dev)
 ms = timeit(lambda i: ops.colsum(hs[i % 2], out))
