@@ -43,11 +43,23 @@ struct Params {
   // backward
   const __nv_bfloat16* o_in; const __nv_bfloat16* do_in; long long lddo;
   __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv; long long lddq, lddk, lddv;
+  int prefetch_stride;        // bwd3: CTA bh prefetches the operands of CTA bh + prefetch_stride into L2 (= resident CTAs of the grid)
 };
 
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a [rows x 128 B] swizzled tile.
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
   return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ float drop_mul(const Params& p, long long bh, int i, int j) {
@@ -428,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
       if (lane == 0) red[warp] = mxt;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mxt = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-      const float e0 = k0ok ? exp2f((s0 - mxt) * sl2) : 0.0f, e1 = k1ok ? exp2f((s1 - mxt) * sl2) : 0.0f;
+      const float e0 = k0ok ? ex2_approx((s0 - mxt) * sl2) : 0.0f, e1 = k1ok ? ex2_approx((s1 - mxt) * sl2) : 0.0f;
       const float ws = warp_sum(e0 + e1);
       if (lane == 0) red[4 + warp] = ws;
       if (k0ok) tail_p[tid] = e0 * drop_mul(p, bh, row, tid);
@@ -475,20 +487,31 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
         mx = fmaxf(mx, acc);
       }
     }
-    for (int c0 = 0; c0 < n_mma; c0 += 32) {       // pass 1: row maximum over the main keys
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + c0, r);
-      tmem_ld_wait_dep(r);
+    {                                              // pass 1: row maximum over the main keys (full blocks carry no per-key predicate)
+      int c0 = 0;
+#pragma unroll 1
+      for (; c0 + 32 <= n_keys; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + c0, r);
+        tmem_ld_wait_dep(r);
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c0 + i < n_keys) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+      }
+      if (c0 < n_keys) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + c0, r);
+        tmem_ld_wait_dep(r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < n_keys) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
     }
     const float mxs = mx * sl2;
     const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, row_ok ? tid : 0);
 #pragma unroll
     for (int t = 0; t < kSmallTailKeys; ++t) {
       if (t < tk) {
-        const float e = exp2f(st[t] * sl2 - mxs);
+        const float e = ex2_approx(fmaf(st[t], sl2, -mxs));
         sum += e;
         st[t] = e * drop_mul(p, bh, row_ok ? tid : 0, 128 + t);
       } else {
@@ -498,28 +521,23 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     // pass 2: P (bf16) into the A-operand tiles, 32 columns per TMEM round trip
     auto emit16 = [&](int c0, const uint32_t* r) {
       uint32_t packed[8];
-      if (c0 + 16 <= n_keys && !p.dropout_thr16) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float e0 = exp2f(__uint_as_float(r[i]) * sl2 - mxs), e1 = exp2f(__uint_as_float(r[i + 1]) * sl2 - mxs);
-          sum += e0 + e1;
-          packed[i >> 1] = pack_bf16x2(e0, e1);
-        }
+      float m[16];
+      if (p.dropout_thr16) {
+        drop_mul16(p, rowkey, c0, m);
       } else {
-        float m[16];
-        if (p.dropout_thr16) {
-          drop_mul16(p, rowkey, c0, m);
-        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) m[i] = 1.0f;
-        }
+        for (int i = 0; i < 16; ++i) m[i] = 1.0f;
+      }
+      const int lim = n_keys - c0;               // >= 16: full block
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float e0 = 0.0f, e1 = 0.0f;
-          if (c0 + i < n_keys) { e0 = exp2f(__uint_as_float(r[i]) * sl2 - mxs); sum += e0; e0 *= m[i]; }
-          if (c0 + i + 1 < n_keys) { e1 = exp2f(__uint_as_float(r[i + 1]) * sl2 - mxs); sum += e1; e1 *= m[i + 1]; }
-          packed[i >> 1] = pack_bf16x2(e0, e1);
+      for (int i = 0; i < 16; i += 2) {
+        float e0 = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mxs)), e1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs));
+        if (lim < 16) {                          // padding keys of the last block
+          e0 = i < lim ? e0 : 0.0f;
+          e1 = i + 1 < lim ? e1 : 0.0f;
         }
+        sum += e0 + e1;
+        packed[i >> 1] = pack_bf16x2(e0 * m[i], e1 * m[i + 1]);
       }
       const uint32_t blk = smem_u32(c0 < 64 ? sQ : sK);
       const int ch = (c0 & 63) >> 3;
@@ -550,13 +568,15 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     mbar_wait(smem_u32(bar_o), 0);
     tc_fence_after();
     const float inv = 1.0f / sum;
-    __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + (row_ok ? tid : 0)) * p.ldo + h * HD;
+    // thread == row for the TMEM read; the warp's 32 rows are staged in its 4 KB of the consumed P block 0 and stored with
+    // 8 lanes per 128-byte row (a row-per-lane store costs 32 line requests per instruction)
+    const uint32_t stage_s = smem_u32(sQ) + warp * 4096;
 #pragma unroll 1
     for (int c0 = 0; c0 < HD; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + c0, r);
       tmem_ld_wait_dep(r);
-      if (row_ok) {
+      {
         float o[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
@@ -577,8 +597,18 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
           uint32_t pk[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) pk[i] = pack_bf16x2(o[8 * g + 2 * i] * inv, o[8 * g + 2 * i + 1] * inv);
-          *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          sts128(stage_s + sw128(lane, (c0 >> 3) + g), pk[0], pk[1], pk[2], pk[3]);
         }
+      }
+    }
+    __syncwarp();
+    {
+      __nv_bfloat16* obase = p.o + (static_cast<long long>(b) * p.Sq + warp * 32) * p.ldo + h * HD;
+      const int nvalid = n_rows - warp * 32;
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it) {
+        const int rr = 4 * it + (lane >> 3);
+        if (rr < nvalid) *reinterpret_cast<uint4*>(obase + rr * p.ldo + 8 * (lane & 7)) = lds128(stage_s + sw128(rr, lane & 7));
       }
     }
     if (row_ok && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + tid] = mx * p.scale + __logf(sum);
@@ -1159,7 +1189,8 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
 // 5.7 k, the one-key tail pass 3.9 k):
 //   * Q, dO, O, K, V all arrive by TMA issued at t = 0 (one box each; O lands in the not-yet-used P block 0 and
 //     D_i = sum_c dO_ic O_ic is computed from shared memory);
-//   * four tail-row warps split the keys (warp 8's lane 0 is also the TMA / MMA issuer);
+//   * five tail-row warps split the keys (warp 8's lane 0 is also the TMA / MMA issuer); the next CTA's operands are
+//     prefetched into L2 while this one computes;
 //   * lean P / dS arithmetic: ex2.approx, masking only as a bitwise fix-up of the last (partial) block, softmax scale
 //     applied when dK / dQ leave instead of per dS element;
 //   * dV / dK of the tail keys are issued with the main gradient MMAs into the (by then free) S columns, so there is no
@@ -1168,7 +1199,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
 //     its instruction footprint is fetch time.
 // TMEM: S [0,144) | dP [160,304) | dK [320,384) | dV [384,448) | dQ [448,512); tail keys: dV_t [0,64) | dK_t [64,128)
 // smem: Q 16K | dO 16K | P 48K (block 0 first holds O) | dS 48K | K 18K | V 18K | barriers | D partials | tail scratch
-constexpr int kThreadsBwd3 = 384;   // warps 0-7 workers (two threads per row), warps 8-11 tail query rows
+constexpr int kThreadsBwd3 = 416;   // warps 0-7 workers (two threads per row), warps 8-12 tail query rows (warp 12: keys >= 128)
 
 #ifdef TVT_ATTN_STAMPS
 __device__ long long g_stamps[3][32];
@@ -1181,50 +1212,48 @@ __device__ long long g_stamps[3][32];
 #define TVT_STAMP(slot) do {} while (0)
 #endif
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lds_f32(uint32_t saddr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
-  return v;
-}
 
-// Rows of a [128 x 32 * pieces] fp32 accumulator -> bf16 global rows (thread == row): out = (acc + sum_t w_t * vec_t) * mul,
-// the rank-1 terms being the tail query rows' contributions (w_t = per-row weight at w_s + t * KC floats, vec_t = 64-float
-// vector at vec_s + t * HD floats).  Deliberately not inlined: one copy serves dK, dV, their tail keys and dQ.
-__device__ __noinline__ void drain_rows(uint32_t taddr, __nv_bfloat16* dst, bool ok, int pieces, float mul, int ntail, uint32_t w_s,
-                                        uint32_t vec_s) {
+// One warp's 32 rows of a [128 x 64] fp32 accumulator -> bf16 global rows: out = (acc + sum_t w_t * vec_t) * mul, the rank-1
+// terms being the tail query rows' contributions (w_t = this lane's row weight at w_s + t * KC floats, vec_t = 64-float vector
+// at vec_s + t * HD floats).  Thread == row for the TMEM read, but a row-per-lane global store costs 32 line requests per
+// instruction (the LSU was the drain's bottleneck), so the warp's rows are staged through 4 KB of swizzled shared memory and
+// stored with 8 lanes per 128-byte row.  Rows [0, nvalid) of the warp are written; row r goes to dst + r * ld.
+// Deliberately not inlined: one copy serves dK, dV, their tail keys and dQ.
+__device__ __noinline__ void drain_rows(uint32_t taddr, __nv_bfloat16* dst, long long ld, int nvalid, float mul, int ntail, uint32_t w_s,
+                                        uint32_t vec_s, uint32_t stage_s) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (int pc = 0; pc < pieces; ++pc) {
+  for (int pc = 0; pc < 2; ++pc) {
     uint32_t r[32];
     tmem_ld_32x32b_x32(taddr + 32 * pc, r);
     tmem_ld_wait_dep(r);
-    if (ok) {
-      float f[32];
+    float f[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
 #pragma unroll 1
-      for (int t = 0; t < ntail; ++t) {
-        const float wj = lds_f32(w_s + t * KC * 4);
+    for (int t = 0; t < ntail; ++t) {
+      const float wj = lds_f32(w_s + t * KC * 4);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const uint4 v = lds128(vec_s + (t * HD + 32 * pc + i) * 4);
-          f[i] += wj * __uint_as_float(v.x);
-          f[i + 1] += wj * __uint_as_float(v.y);
-          f[i + 2] += wj * __uint_as_float(v.z);
-          f[i + 3] += wj * __uint_as_float(v.w);
-        }
+      for (int i = 0; i < 32; i += 4) {
+        const uint4 v = lds128(vec_s + (t * HD + 32 * pc + i) * 4);
+        f[i] += wj * __uint_as_float(v.x);
+        f[i + 1] += wj * __uint_as_float(v.y);
+        f[i + 2] += wj * __uint_as_float(v.z);
+        f[i + 3] += wj * __uint_as_float(v.w);
       }
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(dst + 32 * pc + 8 * g) =
-            make_uint4(pack_bf16x2(f[8 * g] * mul, f[8 * g + 1] * mul), pack_bf16x2(f[8 * g + 2] * mul, f[8 * g + 3] * mul),
-                       pack_bf16x2(f[8 * g + 4] * mul, f[8 * g + 5] * mul), pack_bf16x2(f[8 * g + 6] * mul, f[8 * g + 7] * mul));
     }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      sts128(stage_s + sw128(lane, 4 * pc + g), pack_bf16x2(f[8 * g] * mul, f[8 * g + 1] * mul), pack_bf16x2(f[8 * g + 2] * mul, f[8 * g + 3] * mul),
+             pack_bf16x2(f[8 * g + 4] * mul, f[8 * g + 5] * mul), pack_bf16x2(f[8 * g + 6] * mul, f[8 * g + 7] * mul));
   }
+  __syncwarp();
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int rr = 4 * it + (lane >> 3);
+    if (rr < nvalid) *reinterpret_cast<uint4*>(dst + rr * ld + 8 * (lane & 7)) = lds128(stage_s + sw128(rr, lane & 7));
+  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -1280,9 +1309,24 @@ __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constan
     tmem_relinquish();
   }
   float Li = 0.0f;
-  if (worker) {
-    if (row < n_main) Li = p.lse[static_cast<long long>(bh) * p.Sq + row] * kLog2e;
-  } else if (warp == 9) {
+  if (worker && row < n_main) Li = p.lse[static_cast<long long>(bh) * p.Sq + row] * kLog2e;
+  tc_fence_before();
+  __syncthreads();                  // #1: TMEM base address visible
+  tc_fence_after();
+  if (tid == 0) TVT_STAMP(1);
+  if (warp == 10 && lane == 0) {
+    // the CTA that follows this one on the SM (one resident CTA per SM, so roughly blockIdx + #SMs): pull its operands into L2
+    const int nb = bh + p.prefetch_stride;
+    if (nb < static_cast<int>(gridDim.x)) {
+      const int b2 = nb / p.H, h2 = nb % p.H;
+      tma_prefetch_2d(&tmQ, h2 * HD, b2 * p.Sq);
+      tma_prefetch_2d(&tmK, h2 * HD, b2 * p.Sk);
+      tma_prefetch_2d(&tmdO, h2 * HD, b2 * p.Sq);
+      tma_prefetch_2d(&tmV, h2 * HD, b2 * p.Sk);
+      tma_prefetch_2d(&tmO, h2 * HD, b2 * p.Sq);
+    }
+  }
+  if (warp == 9) {
     for (int t = 0; t < ntail; ++t) {
       const long long grow = static_cast<long long>(b) * p.Sq + n_main + t;
       const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.q_in + grow * p.ldq + h * HD + 2 * lane));
@@ -1298,10 +1342,6 @@ __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constan
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();                  // #1: TMEM base address and tail scratch visible
-  tc_fence_after();
-  if (tid == 0) TVT_STAMP(1);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 160, tdK = tmem_base + 320, tdV = tmem_base + 384, tdQ = tmem_base + 448;
   const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -1337,7 +1377,7 @@ __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constan
     }
     sDh[half * 128 + row] = acc;
   }
-  __syncthreads();                  // #2: D partials visible; O has been read, P block 0 may be overwritten
+  __syncthreads();                  // #2: D partials and tail scratch visible; O has been read, P block 0 may be overwritten
   if (tid == 0) TVT_STAMP(2);
 
   if (worker) {
@@ -1390,15 +1430,15 @@ __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constan
     fence_proxy_async_smem();
     if (tid == 0) TVT_STAMP(4);
   } else if (ntail > 0) {
-    // tail query rows on CUDA cores: tail warp tw takes keys [32 tw, 32 tw + 32) and, beyond 128, [128 + 32 tw, ...)
+    // tail query rows on CUDA cores: tail warp tw takes keys [32 tw, 32 tw + 32) (warp 12: the tail keys 128..)
     const int tw = warp - 8;
     mbar_wait(smem_u32(bar_ld), 0);
-    if (lane == 0) TVT_STAMP(24 + tw);
+    if (lane == 0 && tw < 4) TVT_STAMP(24 + tw);
     for (int t = 0; t < ntail; ++t) {
       const float Dt = tDL[2 * t], Lt = tDL[2 * t + 1];
       const uint64_t rowkey = attn_rowkey(bh, p.Sq, p.Sk, n_main + t);
       float a0 = 0.0f, a1 = 0.0f;
-      for (int jb = 32 * tw; jb < nk; jb += 128) {
+      for (int jb = 32 * tw; jb < nk; jb += 160) {
         const int j = jb + lane;
         if (j < nk) {
           float pm = 0.0f, dsv = 0.0f;
@@ -1442,7 +1482,7 @@ __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constan
       atomicAdd(&tdq[t * HD + 2 * lane], a0);
       atomicAdd(&tdq[t * HD + 2 * lane + 1], a1);
     }
-    if (lane == 0) TVT_STAMP(28 + tw);
+    if (lane == 0 && tw < 4) TVT_STAMP(28 + tw);
   }
   tc_fence_before();
   __syncthreads();                  // #3: P, dS tiles and the tail rows' p / ds vectors complete; S / dP columns free
@@ -1480,35 +1520,37 @@ __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constan
     TVT_STAMP(19);
   }
   if (worker) {
-    // half 0 drains dK (+ ds_t q_t, x scale), half 1 drains dV (+ p_t dO_t); thread == key row
-    __nv_bfloat16* gbase = half ? p.dv : p.dk;
+    // half 0 drains dK (+ ds_t q_t, x scale) then dQ; half 1 drains dV (+ p_t dO_t) then the tail keys.  thread == row;
+    // each warp stages its 32 rows in its own 4 KB of the (by then consumed) P blocks 0 / 1
+    __nv_bfloat16* gbase = (half ? p.dv : p.dk) + static_cast<long long>(b) * p.Sk * (half ? p.lddv : p.lddk) + h * HD;
     const long long gld = half ? p.lddv : p.lddk;
     const uint32_t w_s = smem_u32(half ? tp : tds), vec_s = smem_u32(half ? tdo : tq);
-    const float mul = half ? 1.0f : p.scale;
+    const uint32_t stage_s = smem_u32(sP) + warp * 4096;
+    const int r0 = (warp & 3) * 32;               // first row of this warp's TMEM quadrant
     mbar_wait(smem_u32(bar_g1), 0);
     tc_fence_after();
     if (tid == 0) TVT_STAMP(6);
-    if ((warp & 3) * 32 < p.Sk) {
-      const bool ok = row < p.Sk;
-      drain_rows((half ? tdV : tdK) + lane_addr, gbase + (static_cast<long long>(b) * p.Sk + (ok ? row : 0)) * gld + h * HD, ok, 2, mul, ntail,
-                 w_s + row * 4, vec_s);
-    }
+    if (r0 < p.Sk) drain_rows((half ? tdV : tdK) + lane_addr, gbase + r0 * gld, gld, p.Sk - r0, half ? 1.0f : p.scale, ntail, w_s + row * 4, vec_s, stage_s);
     if (tid == 0) TVT_STAMP(7);
     mbar_wait(smem_u32(bar_g2), 0);
     tc_fence_after();
     if (tid == 0) TVT_STAMP(8);
-    if (nk > 128 && (warp & 3) == 0) {            // tail keys: lanes of the first TMEM quadrant
-      const int key = 128 + row;
-      const bool ok = key < p.Sk;
-      drain_rows(tS + (half ? 0 : 64) + lane_addr, gbase + (static_cast<long long>(b) * p.Sk + (ok ? key : 0)) * gld + h * HD, ok, 2, mul, ntail,
-                 w_s + (ok ? key : 0) * 4, vec_s);
-    }
-    if ((warp & 3) * 32 < n_main) {               // dQ of the main rows: each half takes 32 columns
-      const bool ok = row < n_main;
-      drain_rows(tdQ + 32 * half + lane_addr, p.dq + (static_cast<long long>(b) * p.Sq + (ok ? row : 0)) * p.lddq + h * HD + 32 * half, ok, 1,
-                 p.scale, 0, 0, 0);
+    if (half == 0) {
+      if (r0 < n_main)
+        drain_rows(tdQ + lane_addr, p.dq + (static_cast<long long>(b) * p.Sq + r0) * p.lddq + h * HD, p.lddq, n_main - r0, p.scale, 0, 0, 0, stage_s);
+    } else if (warp == 4 && nk > 128) {           // tail keys 128..: lanes of the first TMEM quadrant, dV_t at S[0,64)
+      const int key = 128 + lane < KC ? 128 + lane : KC - 1;
+      drain_rows(tS, gbase + 128 * gld, gld, p.Sk - 128, 1.0f, ntail, smem_u32(tp) + key * 4, smem_u32(tdo), stage_s);
     }
     if (tid == 0) TVT_STAMP(9);
+  } else if (warp == 12) {
+    if (nk > 128) {                               // dK_t at S[64,128): the other idle warp that may read TMEM lanes 0..31
+      mbar_wait(smem_u32(bar_g2), 0);
+      tc_fence_after();
+      const int key = 128 + lane < KC ? 128 + lane : KC - 1;
+      drain_rows(tS + 64, p.dk + (static_cast<long long>(b) * p.Sk + 128) * p.lddk + h * HD, p.lddk, p.Sk - 128, p.scale, ntail,
+                 smem_u32(tds) + key * 4, smem_u32(tq), smem_u32(sP) + 8 * 4096);
+    }
   } else if (warp == 9) {
     for (int t = 0; t < ntail; ++t) {
       __nv_bfloat16* dqrow = p.dq + (static_cast<long long>(b) * p.Sq + n_main + t) * p.lddq + h * HD;
@@ -1640,6 +1682,7 @@ int launch_bwd(const tvt_attention_bwd_args* a, cudaStream_t s) {
     p.q_in = (const __nv_bfloat16*)a->q; p.ldq = a->ldq;
     const size_t bytes3 = 1024 + 2 * 16384 + 6 * 16384 + 2 * (size_t)KC * 128 + 64 + 256 * 4 + (3 * kMaxTail * HD + 2 * kMaxTail * KC + 2 * kMaxTail) * 4;
     if ((rc = set_smem(bwd3_kernel, bytes3, "tvt_attention_bwd")) != TVT_OK) return rc;
+    p.prefetch_stride = num_sms();
     bwd3_kernel<<<p.B * p.H, kThreadsBwd3, bytes3, s>>>(tq128, tk1, tv1, tdo128, to128, p);
     return check_launch("tvt_attention_bwd");
   }
