@@ -133,6 +133,164 @@ __global__ void __launch_bounds__(kWarps * 32, kChunks <= 4 ? 3 : 1) ln_fwd_kern
   }
 }
 
+// ---- plain-mode forward with the rows staged by the bulk-copy engine -------------------------------------------------
+// ncu on the register-prefetch kernel above: half issue-bound (423 instructions per row at 52 % issue utilisation) and half
+// latency-bound on the two dependent shuffle trees of every row (short-scoreboard stalls), with loads in flight limited by
+// registers.  Here every warp owns a private ring of kRing slots in shared memory, each slot holding a PAIR of consecutive
+// rows fetched by one cp.async.bulk (lane 0 issues, one mbarrier per slot), and normalises both rows of a slot together:
+//   * bytes in flight no longer depend on registers or on the warp's instruction stream;
+//   * each of the two reduction passes (mean, centred sum of squares: torch's arithmetic) runs ONE shuffle tree for both
+//     rows of the pair, i.e. two trees per pair instead of four (a shifted single pass was tried: 5x larger rstd error,
+//     enough to push one fp32-mode gradient of the cross-attention model past 1e-3);
+//   * gamma / beta are read from shared memory once per pair; no column predicates when d fills the chunks exactly.
+// No block-level synchronisation after the prologue.
+constexpr int kRing = 3;
+constexpr int kRingWarps = 4;
+
+__device__ __forceinline__ void bulk_load_rows(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar_s) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar_s, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar_s), "r"(parity) : "memory");
+}
+
+template <typename T, int kChunks, bool kExact>
+__global__ void __launch_bounds__(kRingWarps * 32) ln_fwd_ring_kernel(const FwdParams p) {
+  constexpr int V = Vec16<T>::kN;
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ __align__(16) float gam_s[kChunks * 32 * V], bet_s[kChunks * 32 * V];
+  __shared__ __align__(8) unsigned long long bars[kRingWarps][kRing];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long pair0 = static_cast<long long>(blockIdx.x) * kRingWarps + warp;
+  const long long npairs = (p.rows + 1) >> 1, stride = static_cast<long long>(gridDim.x) * kRingWarps;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.d) * sizeof(T);
+  const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring_raw)) + warp * kRing * 2 * row_bytes;
+  const uint32_t bar_s = static_cast<uint32_t>(__cvta_generic_to_shared(&bars[warp][0]));
+  auto fetch = [&](long long q, int slot) {      // rows 2q, 2q + 1 (the last pair may be a single row)
+    const uint32_t bytes = 2 * q + 1 < p.rows ? 2 * row_bytes : row_bytes;
+    bulk_load_rows(ring_s + slot * 2 * row_bytes, reinterpret_cast<const T*>(p.x) + 2 * q * p.d, bytes, bar_s + 8 * slot);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8 * s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < kRing; ++s)
+      if (pair0 + s * stride < npairs) fetch(pair0 + s * stride, s);
+  }
+  for (int t = threadIdx.x; t < kChunks * 32 * V; t += kRingWarps * 32) {
+    gam_s[t] = t < p.d ? p.gamma[t] : 0.0f;
+    bet_s[t] = t < p.d ? p.beta[t] : 0.0f;
+  }
+  __syncthreads();
+  const float inv_d = 1.0f / p.d;
+  int slot = 0;
+  uint32_t parity = 0;
+  for (long long q = pair0; q < npairs; q += stride) {
+    bar_wait(bar_s + 8 * slot, parity);
+    float v[2][kChunks][V];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = (c * 32 + lane) * V;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (kExact || col < p.d)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                       : "r"(ring_s + (slot * 2 + r) * row_bytes + col * static_cast<uint32_t>(sizeof(T))) : "memory");
+        Vec16<T>::unpack(raw, v[r][c]);
+      }
+    }
+    // two passes over the registers (mean, then centred sum of squares: same arithmetic as torch), one shuffle tree per
+    // pass carrying both rows of the pair
+    float s1[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) s1[r] += v[r][c][i];   // columns beyond d hold zeros
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], o);
+      s1[1] += __shfl_xor_sync(0xffffffffu, s1[1], o);
+    }
+    // every lane's slot data went into the shuffle tree above, so the slot can be refilled: kRing pairs ahead
+    if (lane == 0 && q + kRing * stride < npairs) fetch(q + kRing * stride, slot);
+    const float mean[2] = {s1[0] * inv_d, s1[1] * inv_d};
+    float s2[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = (c * 32 + lane) * V;
+        if (kExact || col < p.d) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float t = v[r][c][i] - mean[r];
+            s2[r] = fmaf(t, t, s2[r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], o);
+      s2[1] += __shfl_xor_sync(0xffffffffu, s2[1], o);
+    }
+    float rstd[2], shift[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      rstd[r] = rsqrtf(s2[r] * inv_d + p.eps);
+      shift[r] = -mean[r] * rstd[r];
+      if (lane == 0 && 2 * q + r < p.rows) {
+        if (p.mean) p.mean[2 * q + r] = mean[r];
+        if (p.rstd) p.rstd[2 * q + r] = rstd[r];
+      }
+    }
+    T* dst = reinterpret_cast<T*>(p.y) + 2 * q * p.d;
+    const bool two = 2 * q + 1 < p.rows;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      if (kExact || col < p.d) {
+        float o0[V], o1[V];
+#pragma unroll
+        for (int i = 0; i < V; i += 4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gam_s + col + i);
+          const float4 b4 = *reinterpret_cast<const float4*>(bet_s + col + i);
+          const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if constexpr (sizeof(T) == 4) {      // fp32 parity mode: torch's (x - mean) * rstd * gamma + beta, rounding for rounding
+              o0[i + u] = (v[0][c][i + u] - mean[0]) * rstd[0] * gm[u] + bt[u];
+              o1[i + u] = (v[1][c][i + u] - mean[1]) * rstd[1] * gm[u] + bt[u];
+            } else {                             // bf16 output: two FMAs per element (the bf16 rounding is 1e4 x any difference)
+              o0[i + u] = fmaf(fmaf(v[0][c][i + u], rstd[0], shift[0]), gm[u], bt[u]);
+              o1[i + u] = fmaf(fmaf(v[1][c][i + u], rstd[1], shift[1]), gm[u], bt[u]);
+            }
+          }
+        }
+        Vec16<T>::store(dst + col, o0);
+        if (two) Vec16<T>::store(dst + p.d + col, o1);
+      }
+    }
+    if (++slot == kRing) { slot = 0; parity ^= 1; }
+  }
+}
+
 struct BwdParams {
   const void* dy;     // grad wrt LN output [rows, d]
   const void* x;      // pre-LN input [rows, d]
@@ -287,6 +445,164 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kChunks <= 4 ? 3 : 1) ln_bwd_k
   }
 }
 
+// ---- plain-mode backward on the same bulk-copy ring ------------------------------------------------------------------------
+// ncu on ln_bwd_kernel: 793 instructions per row at 48 % issue utilisation, i.e. instruction-bound (both passes unpack dy and
+// x, the second pass recomputes x_hat and dy * gamma, every column access is predicated, and the prefetched rows cost 48
+// registers).  Here a slot of the warp's ring holds the dy row, the x row and (if given) the residual-gradient row, fetched
+// by cp.async.bulk; x_hat and dy * gamma are computed once and kept (the registers the prefetch used to take), so the second
+// pass is two FMAs per element, and the next row's mean / rstd are fetched one iteration ahead.
+constexpr int kRingB = 3;
+
+template <typename T, int kChunks, bool kExact>
+__global__ void __launch_bounds__(kRingWarps * 32) ln_bwd_ring_kernel(const BwdParams p) {
+  constexpr int V = Vec16<T>::kN;
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ __align__(16) float gam_s[kChunks * 32 * V];
+  __shared__ __align__(8) unsigned long long bars[kRingWarps][kRingB];
+  __shared__ float red[kRingWarps][32 * V + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * kRingWarps + warp;
+  const long long nwarps = static_cast<long long>(gridDim.x) * kRingWarps;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.d) * sizeof(T);
+  const int nsrc = p.dres ? 3 : 2;
+  const uint32_t slot_bytes = nsrc * row_bytes;
+  const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring_raw)) + warp * kRingB * slot_bytes;
+  const uint32_t bar_s = static_cast<uint32_t>(__cvta_generic_to_shared(&bars[warp][0]));
+  auto fetch = [&](long long r, int slot) {
+    const uint32_t dst = ring_s + slot * slot_bytes, bar = bar_s + 8 * slot;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(slot_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(reinterpret_cast<const T*>(p.dy) + r * p.d), "r"(row_bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst + row_bytes), "l"(reinterpret_cast<const T*>(p.x) + r * p.d), "r"(row_bytes), "r"(bar) : "memory");
+    if (p.dres)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + 2 * row_bytes), "l"(reinterpret_cast<const T*>(p.dres) + r * p.d), "r"(row_bytes), "r"(bar) : "memory");
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kRingB; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8 * s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < kRingB; ++s)
+      if (warp0 + s * nwarps < p.rows) fetch(warp0 + s * nwarps, s);
+  }
+  for (int t = threadIdx.x; t < kChunks * 32 * V; t += kRingWarps * 32) gam_s[t] = t < p.d ? p.gamma[t] : 0.0f;
+  __syncthreads();
+  float acc_g[kChunks][V], acc_b[kChunks][V], acc_z[kChunks][V];
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc_g[c][i] = acc_b[c][i] = acc_z[c][i] = 0.0f;
+  }
+  const float inv_d = 1.0f / p.d;
+  float mean_n = 0.0f, rstd_n = 0.0f;
+  if (warp0 < p.rows) { mean_n = p.mean[warp0]; rstd_n = p.rstd[warp0]; }
+  int slot = 0;
+  uint32_t parity = 0;
+  for (long long row = warp0; row < p.rows; row += nwarps) {
+    const float rstd = rstd_n, shift = -mean_n * rstd_n;
+    if (row + nwarps < p.rows) { mean_n = p.mean[row + nwarps]; rstd_n = p.rstd[row + nwarps]; }
+    bar_wait(bar_s + 8 * slot, parity);
+    const uint32_t base = ring_s + slot * slot_bytes;
+    float xh[kChunks][V], g[kChunks][V];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      uint4 rdy = make_uint4(0, 0, 0, 0), rx = make_uint4(0, 0, 0, 0);
+      if (kExact || col < p.d) {
+        const uint32_t a = base + col * static_cast<uint32_t>(sizeof(T));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rdy.x), "=r"(rdy.y), "=r"(rdy.z), "=r"(rdy.w) : "r"(a) : "memory");
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rx.x), "=r"(rx.y), "=r"(rx.z), "=r"(rx.w) : "r"(a + row_bytes) : "memory");
+      }
+      float dyv[V], xv[V];
+      Vec16<T>::unpack(rdy, dyv);
+      Vec16<T>::unpack(rx, xv);
+#pragma unroll
+      for (int i = 0; i < V; i += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gam_s + col + i);
+        const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float h = (kExact || col < p.d) ? fmaf(xv[i + u], rstd, shift) : 0.0f;
+          const float gg = dyv[i + u] * gm[u];
+          xh[c][i + u] = h;
+          g[c][i + u] = gg;
+          acc_g[c][i + u] = fmaf(dyv[i + u], h, acc_g[c][i + u]);
+          acc_b[c][i + u] += dyv[i + u];
+          s1 += gg;
+          s2 = fmaf(gg, h, s2);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float A = -rstd * s2 * inv_d, B = -rstd * s1 * inv_d;
+    T* dx_row = reinterpret_cast<T*>(p.dx) + row * p.d;
+    T* dz_row = p.dz ? reinterpret_cast<T*>(p.dz) + row * p.d : nullptr;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int col = (c * 32 + lane) * V;
+      if (kExact || col < p.d) {
+        float o[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = fmaf(xh[c][i], A, fmaf(g[c][i], rstd, B));
+        if (p.dres) {
+          uint4 rr;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w)
+                       : "r"(base + 2 * row_bytes + col * static_cast<uint32_t>(sizeof(T))) : "memory");
+          float rv[V];
+          Vec16<T>::unpack(rr, rv);
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] += rv[i];
+        }
+        Vec16<T>::store(dx_row + col, o);
+        if (p.dropout_thr16) {   // dropout_ld % 4 == 0 and col % 4 == 0: one hash per 4 consecutive elements
+          const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.dropout_ld + col) >> 2;
+#pragma unroll
+          for (int q = 0; q < V / 4; ++q) {
+            const uint64_t bits = dropout_bits4(p.dropout_seed, e4 + q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o[4 * q + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? o[4 * q + i] * p.dropout_scale : 0.0f;
+          }
+        }
+        if (dz_row) Vec16<T>::store(dz_row + col, o);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc_z[c][i] += o[i];
+      }
+    }
+    // the slot (incl. its residual-gradient row) has been consumed by every lane: refill it kRingB rows ahead
+    __syncwarp();
+    if (lane == 0 && row + kRingB * nwarps < p.rows) fetch(row + kRingB * nwarps, slot);
+    if (++slot == kRingB) { slot = 0; parity ^= 1; }
+  }
+  // CTA-level reduction of the column partials through shared memory, then one atomic per column.
+  for (int which = 0; which < 3; ++which) {
+    float* out = which == 0 ? p.dgamma : (which == 1 ? p.dbeta : p.dbias);
+    if (!out) continue;  // uniform
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        red[warp][lane * V + i] = which == 0 ? acc_g[c][i] : (which == 1 ? acc_b[c][i] : acc_z[c][i]);
+      __syncthreads();
+      for (int t = threadIdx.x; t < 32 * V; t += kRingWarps * 32) {
+        float sacc = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kRingWarps; ++w) sacc += red[w][t];
+        const int col = c * 32 * V + t;
+        if (col < p.d) atomicAdd(out + col, sacc);
+      }
+    }
+  }
+}
+
 template <typename T, template <typename, int> class Launcher, typename P>
 static int dispatch_chunks(const P& p, int d, cudaStream_t s) {
   constexpr int V = Vec16<T>::kN;
@@ -317,6 +633,51 @@ struct FwdLauncher {
   static int run(const FwdParams& p, cudaStream_t s) {
     ln_fwd_kernel<T, C><<<grid_for(ln_fwd_kernel<T, C>, kWarps * 32, p.rows, kWarps), kWarps * 32, 0, s>>>(p);
     return check_launch("tvt_layernorm_fwd");
+  }
+};
+template <typename T, int C>
+struct FwdRingLauncher {
+  template <bool kExact>
+  static int launch(const FwdParams& p, cudaStream_t s) {
+    auto kern = ln_fwd_ring_kernel<T, C, kExact>;
+    const size_t bytes = static_cast<size_t>(kRingWarps) * kRing * 2 * p.d * sizeof(T);
+    static bool attr_done = false;   // benign race: the attribute call is idempotent
+    if (!attr_done) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return check_launch("tvt_layernorm_fwd");
+      attr_done = true;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRingWarps * 32, bytes) != cudaSuccess || occ < 1) occ = 2;
+    const long long want = ((p.rows + 1) / 2 + kRingWarps - 1) / kRingWarps;
+    const long long cap = static_cast<long long>(num_sms()) * occ;
+    kern<<<static_cast<int>(want < cap ? want : cap), kRingWarps * 32, bytes, s>>>(p);
+    return check_launch("tvt_layernorm_fwd");
+  }
+  static int run(const FwdParams& p, cudaStream_t s) {
+    return p.d == C * 32 * Vec16<T>::kN ? launch<true>(p, s) : launch<false>(p, s);
+  }
+};
+template <typename T, int C>
+struct BwdRingLauncher {
+  template <bool kExact>
+  static int launch(const BwdParams& p, cudaStream_t s) {
+    auto kern = ln_bwd_ring_kernel<T, C, kExact>;
+    const size_t bytes = static_cast<size_t>(kRingWarps) * kRingB * (p.dres ? 3 : 2) * p.d * sizeof(T);
+    static bool attr_done = false;   // benign race: the attribute call is idempotent
+    if (!attr_done) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return check_launch("tvt_layernorm_bwd");
+      attr_done = true;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRingWarps * 32, bytes) != cudaSuccess || occ < 1) occ = 2;
+    // fewer, fatter CTAs than rows would allow: each ends with d atomics per output vector
+    const long long want = ((p.rows + 3) / 4 + kRingWarps - 1) / kRingWarps;
+    const long long cap = static_cast<long long>(num_sms()) * occ;
+    kern<<<static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap), kRingWarps * 32, bytes, s>>>(p);
+    return check_launch("tvt_layernorm_bwd");
+  }
+  static int run(const BwdParams& p, cudaStream_t s) {
+    return p.d == C * 32 * Vec16<T>::kN ? launch<true>(p, s) : launch<false>(p, s);
   }
 };
 template <typename T, int C>
@@ -360,6 +721,11 @@ extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) 
     p.dropout_seed = a->dropout_seed;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // plain rows of up to 4 chunks (d <= 1024 bf16 / 512 fp32): bulk-copy ring kernel; embed mode and wider rows: register-prefetch kernel
+  const int vec = a->dtype == TVT_F32 ? 4 : 8;
+  if (a->seq_len == 0 && p.d <= 4 * 32 * vec)
+    return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::FwdRingLauncher>(p, p.d, s)
+                               : ln::dispatch_chunks<__nv_bfloat16, ln::FwdRingLauncher>(p, p.d, s);
   return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::FwdLauncher>(p, p.d, s)
                              : ln::dispatch_chunks<__nv_bfloat16, ln::FwdLauncher>(p, p.d, s);
 }
@@ -398,6 +764,10 @@ extern "C" int tvt_layernorm_bwd(const tvt_layernorm_bwd_args* a, void* stream) 
   TVT_REQUIRE(!(a->dres && (a->dz || a->seq_len > 0 || a->dropout_p > 0.0f)), "tvt_layernorm_bwd: dres cannot be combined with dz / embed mode / dropout");
   TVT_REQUIRE(al16(a->dres), "tvt_layernorm_bwd: dres must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int vec = a->dtype == TVT_F32 ? 4 : 8;
+  if (a->seq_len == 0 && p.d <= 4 * 32 * vec)
+    return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::BwdRingLauncher>(p, p.d, s)
+                               : ln::dispatch_chunks<__nv_bfloat16, ln::BwdRingLauncher>(p, p.d, s);
   return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::BwdLauncher>(p, p.d, s)
                              : ln::dispatch_chunks<__nv_bfloat16, ln::BwdLauncher>(p, p.d, s);
 }
