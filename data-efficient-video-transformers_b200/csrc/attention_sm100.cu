@@ -354,8 +354,8 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
   uint64_t* bar_s = bars + 2;
   uint64_t* bar_o = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  float* tail_q = reinterpret_cast<float*>(bars + 8);   // [8 + 64] reduction scratch of the tail-row path
-  float* tail_p = tail_q + 8 + HD;                      // [KC] probabilities of the current tail row
+  float* tail_q = reinterpret_cast<float*>(bars + 8);   // [8 + 4 * 64] reduction scratch of the tail-row path
+  float* tail_p = tail_q + 8 + 4 * HD;                  // [KC] probabilities of the current tail row
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool issuer = warp == 4 && lane == 0;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     //      (instead of a dedicated warp) keeps the four SM sub-partitions evenly loaded: every CTA's extra warp
     //      would land on the same sub-partition, which became the bottleneck with four resident CTAs.
     float* red = tail_q;                 // [8]   cross-warp max / sum
-    float* part = tail_q + 8;            // [64]  P V partial of the upper thread half
+    float* part = tail_q + 8;            // [4][64] P V partials of the four warps
     // the tail query row comes straight from global memory: fetch it before waiting for the K / V tiles
     uint4 qraw[8];
     {
@@ -447,15 +447,34 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
       if (k1ok) tail_p[128 + tid] = e1 * drop_mul(p, bh, row, 128 + tid);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const float sumt = red[4] + red[5] + red[6] + red[7];
-      // P V: thread (c, half) sums the keys of its parity for output column c
-      const int c = tid & 63, half = tid >> 6;
-      float acc = 0.0f;
-      for (int j = half; j < p.Sk; j += 2) acc += tail_p[j] * __bfloat162float(*sw_elem(sV, j, c));
-      if (half == 1) part[c] = acc;
+      // P V: lane = (key group, 16-byte column chunk); a thread takes every 16th key with a 128-bit V read, the warp's four
+      // key groups are folded with two shuffle steps and the four warps through shared memory
+      {
+        const int ch = lane & 7;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+        for (int j = warp * 4 + (lane >> 3); j < p.Sk; j += 16) {
+          const float pj = tail_p[j];
+          float vf[8];
+          Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(j, ch)), vf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, vf[i], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+          acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+        }
+        if (lane < 8) {
+          *reinterpret_cast<float4*>(part + warp * HD + ch * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(part + warp * HD + ch * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (half == 0) {
+      if (tid < HD) {
         __nv_bfloat16* orow = p.o + (static_cast<long long>(b) * p.Sq + row) * p.ldo + h * HD;
-        orow[c] = __float2bfloat16_rn((acc + part[c]) / sumt);
+        orow[tid] = __float2bfloat16_rn((part[tid] + part[HD + tid] + part[2 * HD + tid] + part[3 * HD + tid]) / sumt);
         if (tid == 0 && p.lse) p.lse[static_cast<long long>(bh) * p.Sq + row] = mxt * p.scale + __logf(sumt);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");   // scratch reused by the next tail row
@@ -521,24 +540,23 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     // pass 2: P (bf16) into the A-operand tiles, 32 columns per TMEM round trip
     auto emit16 = [&](int c0, const uint32_t* r) {
       uint32_t packed[8];
-      float m[16];
-      if (p.dropout_thr16) {
-        drop_mul16(p, rowkey, c0, m);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) m[i] = 1.0f;
-      }
+      float e[16];
       const int lim = n_keys - c0;               // >= 16: full block
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        float e0 = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mxs)), e1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, -mxs));
-        if (lim < 16) {                          // padding keys of the last block
-          e0 = i < lim ? e0 : 0.0f;
-          e1 = i + 1 < lim ? e1 : 0.0f;
-        }
-        sum += e0 + e1;
-        packed[i >> 1] = pack_bf16x2(e0 * m[i], e1 * m[i + 1]);
+      for (int i = 0; i < 16; ++i) {
+        e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mxs));
+        if (lim < 16) e[i] = i < lim ? e[i] : 0.0f;   // padding keys of the last block
       }
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) sum += (e[i] + e[i + 1]) + (e[i + 2] + e[i + 3]);
+      if (p.dropout_thr16) {
+        float m[16];
+        drop_mul16(p, rowkey, c0, m);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] *= m[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) packed[i >> 1] = pack_bf16x2(e[i], e[i + 1]);
       const uint32_t blk = smem_u32(c0 < 64 ? sQ : sK);
       const int ch = (c0 & 63) >> 3;
       sts128(blk + sw128(tid, ch), packed[0], packed[1], packed[2], packed[3]);
@@ -1641,7 +1659,7 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
   if ((rc = make_map(&tk, a->k, a->batch * a->sk, w, a->ldk, p.kv_box)) != TVT_OK) return rc;
   if ((rc = make_map(&tv, a->v, a->batch * a->sk, w, a->ldv, p.kv_box)) != TVT_OK) return rc;
   if (p.Sq <= 128 + kMaxTail && p.Sk <= 128 + kSmallTailKeys) {
-    const size_t bytes_s = 1024 + 16384 + 2 * (size_t)KC * 128 + 64 + (8 + HD + KC) * 4;   // 54 KB: 4 CTAs / SM
+    const size_t bytes_s = 1024 + 16384 + 2 * (size_t)KC * 128 + 64 + (8 + 4 * HD + KC) * 4;   // 55 KB: 4 CTAs / SM
     if ((rc = set_smem(fwd_small_kernel, bytes_s, "tvt_attention_fwd")) != TVT_OK) return rc;
     fwd_small_kernel<<<p.B * p.H, kThreads, bytes_s, s>>>(tq, tk, tv, p);
     return check_launch("tvt_attention_fwd");
