@@ -193,8 +193,14 @@ class Mode:
         K = W.shape[1]
         wh, wl = self.weight(W, rows)
         dx = self.empty(M, K, device=dyp[0].device)
+        alpha = 1.0
+        if relu_mask is not None and dropout_p > 0.0:
+            # relu_mask is the activation AFTER forward dropout: dropped elements are already zero in it, so the mask test
+            # covers both gates and the dropout stage reduces to its constant 1 / (1 - p) (no hash in the epilogue)
+            thr16 = int(dropout_p * 65536.0 + 0.5)
+            alpha, dropout_p = 65536.0 / (65536.0 - thr16), 0.0
         gemm(dyp[0], wh, M, K, N, a_lo=dyp[1], b_lo=wl, lda=_rowmajor(dyp[0]), ldb=_rowmajor(wh), b_mn=True,
-             residual=residual, relu_mask=relu_mask, gelu_gate=gelu_gate, dropout_p=dropout_p, seed=seed,
+             residual=residual, relu_mask=relu_mask, gelu_gate=gelu_gate, dropout_p=dropout_p, seed=seed, alpha=alpha,
              out_f32=dx if self.fp32 else None, out_bf16=None if self.fp32 else dx)
         return dx
 
