@@ -383,6 +383,8 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  pdl_wait();      // barrier init and TMEM allocation overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (issuer) {
     mbar_arrive_expect_tx(smem_u32(bar_kv), 2 * p.sk_pad * 128);
@@ -1307,6 +1309,8 @@ __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constan
   const int n_main = p.Sq < 128 ? p.Sq : 128;       // valid rows of the tensor-core tile
   const int ntail = p.Sq - n_main;                  // rows handled by the tail warps
   const int nk = p.sk_pad;                          // padded keys (multiple of 16, <= KC)
+  pdl_wait();      // the operand TMAs are issued in the prologue, so wait first: only the launch latency is overlapped
+  pdl_trigger();
   if (tid == 0) TVT_STAMP(0);
   if (issuer) {
     mbar_init(smem_u32(bar_ld), 1);
@@ -1661,7 +1665,7 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
   if (p.Sq <= 128 + kMaxTail && p.Sk <= 128 + kSmallTailKeys) {
     const size_t bytes_s = 1024 + 16384 + 2 * (size_t)KC * 128 + 64 + (8 + 4 * HD + KC) * 4;   // 55 KB: 4 CTAs / SM
     if ((rc = set_smem(fwd_small_kernel, bytes_s, "tvt_attention_fwd")) != TVT_OK) return rc;
-    fwd_small_kernel<<<p.B * p.H, kThreads, bytes_s, s>>>(tq, tk, tv, p);
+    if (launch_pdl(fwd_small_kernel, p.B * p.H, kThreads, bytes_s, s, 1, tq, tk, tv, p) != cudaSuccess) return check_launch("tvt_attention_fwd");
     return check_launch("tvt_attention_fwd");
   }
   const int kv = ((p.sk_pad * 128) + 1023) & ~1023;
@@ -1701,7 +1705,7 @@ int launch_bwd(const tvt_attention_bwd_args* a, cudaStream_t s) {
     const size_t bytes3 = 1024 + 2 * 16384 + 6 * 16384 + 2 * (size_t)KC * 128 + 64 + 256 * 4 + (3 * kMaxTail * HD + 2 * kMaxTail * KC + 2 * kMaxTail) * 4;
     if ((rc = set_smem(bwd3_kernel, bytes3, "tvt_attention_bwd")) != TVT_OK) return rc;
     p.prefetch_stride = num_sms();
-    bwd3_kernel<<<p.B * p.H, kThreadsBwd3, bytes3, s>>>(tq128, tk1, tv1, tdo128, to128, p);
+    launch_pdl(bwd3_kernel, p.B * p.H, kThreadsBwd3, bytes3, s, 1, tq128, tk1, tv1, tdo128, to128, p);
     return check_launch("tvt_attention_bwd");
   }
   if (p.Sq <= 128 + kMaxTail) {

@@ -402,6 +402,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (kCta2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the prologue above overlapped the previous kernel's tail; its results are visible from here on
+  pdl_trigger();
 
   const int num_m = (p.M + BM * kCtas - 1) / (BM * kCtas);
   const int num_n = (p.N + BN - 1) / BN;
@@ -814,26 +816,10 @@ static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) 
   const long long total = num_m * num_n * p.splits;   // tiles (of a CTA pair when kCta2)
   const long long slots = num_sms() / kCtas;
   const int grid = static_cast<int>(total < slots ? total : slots) * kCtas;
-  if constexpr (kCta2) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = C::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmAlo, tmB, tmBlo, tmSide, p);
-    if (e != cudaSuccess) {
-      set_last_error("tvt_gemm: cluster launch failed: %s", cudaGetErrorString(e));
-      return TVT_ECUDA;
-    }
-  } else {
-    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, tmSide, p);
+  const cudaError_t e = launch_pdl(kern, grid, kThreads, C::kSmemBytes, stream, kCta2 ? 2 : 1, tmA, tmAlo, tmB, tmBlo, tmSide, p);
+  if (e != cudaSuccess) {
+    set_last_error("tvt_gemm: launch failed: %s", cudaGetErrorString(e));
+    return TVT_ECUDA;
   }
   return check_launch("tvt_gemm");
 }

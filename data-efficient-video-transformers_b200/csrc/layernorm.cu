@@ -3,6 +3,7 @@
 // "Embed" row mapping fuses SimpleTransformer.add_pos_cls (reference src/models/transformer.py:74-82):
 // CLS concat + positional-encoding add + (dropout) + LayerNorm in one pass, and its backward scatter.
 #include "tvt_common.cuh"
+#include "tvt_ptx.cuh"
 
 namespace tvt {
 namespace ln {
@@ -184,6 +185,10 @@ __global__ void __launch_bounds__(kRingWarps * 32) ln_fwd_ring_kernel(const FwdP
 #pragma unroll
     for (int s = 0; s < kRing; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8 * s) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kRing; ++s)
       if (pair0 + s * stride < npairs) fetch(pair0 + s * stride, s);
@@ -483,6 +488,10 @@ __global__ void __launch_bounds__(kRingWarps * 32) ln_bwd_ring_kernel(const BwdP
 #pragma unroll
     for (int s = 0; s < kRingB; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8 * s) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kRingB; ++s)
       if (warp0 + s * nwarps < p.rows) fetch(warp0 + s * nwarps, s);
@@ -650,7 +659,7 @@ struct FwdRingLauncher {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRingWarps * 32, bytes) != cudaSuccess || occ < 1) occ = 2;
     const long long want = ((p.rows + 1) / 2 + kRingWarps - 1) / kRingWarps;
     const long long cap = static_cast<long long>(num_sms()) * occ;
-    kern<<<static_cast<int>(want < cap ? want : cap), kRingWarps * 32, bytes, s>>>(p);
+    launch_pdl(kern, static_cast<int>(want < cap ? want : cap), kRingWarps * 32, bytes, s, 1, p);
     return check_launch("tvt_layernorm_fwd");
   }
   static int run(const FwdParams& p, cudaStream_t s) {
@@ -673,7 +682,7 @@ struct BwdRingLauncher {
     // fewer, fatter CTAs than rows would allow: each ends with d atomics per output vector
     const long long want = ((p.rows + 3) / 4 + kRingWarps - 1) / kRingWarps;
     const long long cap = static_cast<long long>(num_sms()) * occ;
-    kern<<<static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap), kRingWarps * 32, bytes, s>>>(p);
+    launch_pdl(kern, static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap), kRingWarps * 32, bytes, s, 1, p);
     return check_launch("tvt_layernorm_bwd");
   }
   static int run(const BwdParams& p, cudaStream_t s) {
