@@ -245,6 +245,7 @@ def main():
         run_reference(args, w, rank)
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
     import torch.distributed as dist
     import tvt_b200
     from tvt_b200 import capi, ddp
