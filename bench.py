@@ -14,6 +14,7 @@ composition) on a bounded sample of the same workload on this box's host cores.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -275,12 +276,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(run_one, steps):
+    def timed(run_one, steps, finish=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for i in range(steps):
             run_one(i)
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -303,18 +306,37 @@ def main():
 
     # ---- leg 2: end to end from pinned host batches, copies prefetched on a side stream
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [None, None]
+    # two preallocated device slots (no allocator traffic in the loop); slot i % 2 is refilled for step i + 2 only after
+    # step i, its last reader, has finished on the compute stream
+    slots = [([torch.empty_like(x, device=dev) for x in xs], torch.empty_like(y, device=dev)) for xs, y in host]
+    slot_free = [None, None]
 
     def prefetch(i):
+        if slot_free[i % 2] is not None:
+            copy_stream.wait_event(slot_free[i % 2])
         with torch.cuda.stream(copy_stream):
             xs, y = host[i % 2]
-            slots[i % 2] = ([x.to(dev, non_blocking=True) for x in xs], y.to(dev, non_blocking=True))
+            dxs, dy_ = slots[i % 2]
+            for dst, src in zip(dxs, xs):
+                dst.copy_(src, non_blocking=True)
+            dy_.copy_(y, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return ev
 
     losses = []
-    state = {"ev": None}
+    state = {"ev": None, "pending": None}
+    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def read_pending():
+        # device -> host read of a step's loss: the copy into pinned memory was enqueued right behind that step; it is
+        # collected one step later (as a training loop logs), after the NEXT step has been enqueued, so the read never
+        # drains the GPU.  Every step's loss is read inside the timed region (finish() collects the last one).
+        if state["pending"] is not None:
+            ev, buf = state["pending"]
+            ev.synchronize()
+            losses.append(float(buf[0]))
+            state["pending"] = None
 
     def e2e_one(i):
         if state["ev"] is None:
@@ -323,13 +345,19 @@ def main():
         xs, y = slots[i % 2]
         state["ev"] = prefetch(i + 1)                       # next step's inputs copy while this step computes
         loss = gpu_step(w, model, reducer, opt, xs, y)
-        for t in xs:
-            t.record_stream(torch.cuda.current_stream())
-        losses.append(loss.item())                          # device -> host read of the step's result
+        buf = loss_host[i % 2]
+        buf.copy_(loss.detach().reshape(1).float(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot_free[i % 2] = ev                               # this step was the slot's last reader
+        read_pending()                                      # step i - 1's loss, now that step i is in the queue
+        state["pending"] = (ev, buf)
 
     e2e_one(0)
+    read_pending()
     state["ev"] = None
-    ms_e2e = timed(e2e_one, args.steps)
+    ms_e2e = timed(e2e_one, args.steps, finish=read_pending)
+    assert len(losses) == args.steps + 1 and all(math.isfinite(v) for v in losses), "e2e leg: a step's loss was not read back"
 
     # ---- instrumented step: CUDA events around every kernel-launching C-ABI call (not part of the timings)
     breakdown = capi.profile_step(lambda: gpu_step(w, model, reducer, opt, *resident[0]))
@@ -366,7 +394,8 @@ def main():
                    "parallelism": f"dp{world}", "l2": "inputs larger than L2 (%.0f MB per step, two alternating batches)" % (h2d_bytes / 1e6),
                    "gflop_per_clip_step": round(fl / 1e9, 2)},
         "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e, 3)},
+                "ms_per_step": round(ms_e2e, 3),
+                "loss_read": "every step, via pinned memory, collected one step later (after the next step is enqueued); the last inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "model_tflops": round(value / world * fl / 1e12, 1),
@@ -375,6 +404,20 @@ def main():
                      "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": traffic, "peak_source": peak_src,
                      "launches_per_step": gemm["calls"], "share_of_kernel_time": round(gemm["ms"] / total_ms, 4)},
     }
+    # BASELINE.json's second metric: attention TFLOP/s against the bf16 peak (un-padded algorithmic FLOPs of every attention
+    # launch of the instrumented step).  At S = frames + 1 <= 129 and head_dim 64 the kernels have S / 2 FLOP per HBM byte, below
+    # the ridge, so the bandwidth figure (q, k, v, o / their gradients, bf16) is the roofline that actually bounds them.
+    n_tok, burst = B * (w["frames"] + 1), peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained", 1400.0))
+    att = {}
+    for name, tensors in (("fwd", 4), ("bwd", 8)):
+        v = breakdown.get(f"tvt_attention_{name}")
+        if v and v["ms"] > 0:
+            tf = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            gbs = v["calls"] * tensors * n_tok * w["d"] * 2 / (v["ms"] * 1e-3) / 1e9
+            att[name] = {"tflops": round(tf, 1), "frac_of_bf16_peak": round(tf / burst, 4), "hbm_gbs": round(gbs, 1),
+                         "frac_of_hbm_peak": round(gbs / peaks.get("hbm_gbs", 6500.0), 4), "launches_per_step": v["calls"],
+                         "us_per_launch": round(v["ms"] * 1e3 / v["calls"], 1)}
+    line["attention"] = att
     if not args.no_cpu_baseline:
         sample = args.cpu_clips or max(1, min(B, int(2.5e11 / fl) or 1))
         cps, dt, cores = time_oracle(w, sample, 2, 1)
