@@ -246,14 +246,26 @@ def main():
         run_reference(args, w, rank)
         return
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
     import torch.distributed as dist
     import tvt_b200
     from tvt_b200 import capi, ddp
-    rank, local, world = ddp.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the tvt arm has no CPU path (use --impl reference for the CPU oracle)")
-    dev = torch.device("cuda", local)
+    # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG=VERSION/WARN ignore
+    # NCCL_DEBUG_FILE): create it now, with file descriptor 1 pointed at stderr, so stdout carries the JSON line only
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local, world = ddp.init_from_env()
+        dev = torch.device("cuda", local)
+        if world > 1:
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     capi.load()
     if capi.load().tvt_device_check() != 0:
         raise SystemExit("bench.py: " + capi.last_error())
