@@ -74,6 +74,11 @@ class SpatialPoolArgs(C.Structure):
                 ("col_offset", i64), ("dtype", i32), ("out_dtype", i32)]
 
 
+class SpatialPoolBwdArgs(C.Structure):
+    _fields_ = [("dpooled", vp), ("dx", vp), ("frames", i64), ("channels", i64), ("hw", i64), ("ld", i64),
+                ("col_offset", i64), ("dtype", i32), ("reserved", i32)]
+
+
 class DistillLossArgs(C.Structure):
     _fields_ = [("student", vp), ("teacher", vp), ("target", vp), ("losses", vp), ("dlogits", vp), ("batch", i64),
                 ("classes", i64), ("w_bce", f32), ("w_ce", f32), ("w_kl", f32), ("temperature", f32), ("grad_scale", f32)]
@@ -147,6 +152,7 @@ ENTRY_POINTS = {
     "tvt_pyramid_pool_fwd": PyramidPoolFwdArgs,
     "tvt_pyramid_pool_bwd": PyramidPoolBwdArgs,
     "tvt_spatial_pool_fwd": SpatialPoolArgs,
+    "tvt_spatial_pool_bwd": SpatialPoolBwdArgs,
     "tvt_distill_loss": DistillLossArgs,
     "tvt_pyramid_head": PyramidHeadArgs,
     "tvt_colsum": ColsumArgs,

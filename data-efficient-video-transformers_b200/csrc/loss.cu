@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(128) distill_kernel(const Params p) {
     int cand = (tmax == wmax) ? targ : 0x7fffffff;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
-    label = cand;
+    // a teacher row that is all NaN / -inf leaves no candidate (no lane compares equal): clamp to class 0 instead of indexing
+    // s[INT_MAX] (torch.argmax returns a valid index for such rows too)
+    label = (cand < 0 || cand >= p.C) ? 0 : cand;
     tmax = wmax;
     dot = warp_sum(dot); ns = warp_sum(ns); nt = warp_sum(nt);
     float e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;

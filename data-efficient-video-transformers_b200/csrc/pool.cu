@@ -2,9 +2,10 @@
 //   tvt_pyramid_pool_fwd / _bwd : every sum_group scale of Reasoning.forward (reference
 //                                 src/models/TPN.py:64-72,106-110) in ONE pass over the frame tokens,
 //                                 with the leading ReLU of each relation MLP (TPN.py:89) fused.
-//   tvt_spatial_pool_fwd        : AvgPool2d to 1x1 of Feature_Pyramid_{low,Mid,High} (TPN.py:5,19,32).
+//   tvt_spatial_pool_fwd / _bwd : AvgPool2d to 1x1 of Feature_Pyramid_{low,Mid,High} (TPN.py:5,19,32) and its gradient.
 // Pure bandwidth kernels: 16-byte vector IO, each input element read exactly once.
 #include "tvt_common.cuh"
+#include "tvt_ptx.cuh"
 
 namespace tvt {
 namespace pool {
@@ -102,9 +103,12 @@ __global__ void __launch_bounds__(256) bwd_kernel(const BwdParams p) {
   }
 }
 
-struct SpatialParams { const void* x; void* out; long long frames, C, hw, ld_out, col_off; int out_f32; };
+struct SpatialParams {
+  const void* x; void* out; long long frames, C, hw, ld_out, col_off; int out_f32;
+  long long rows_per_tile, ntiles;   // tiled kernel only
+};
 
-// One warp per (frame, channel): coalesced read of the HW contiguous elements, shuffle reduce.
+// Fallback (unaligned base, rows longer than a tile): one warp per (frame, channel), coalesced scalar reads, shuffle reduce.
 template <typename T>
 __global__ void __launch_bounds__(256) spatial_kernel(const SpatialParams p) {
   const int lane = threadIdx.x & 31;
@@ -122,6 +126,130 @@ __global__ void __launch_bounds__(256) spatial_kernel(const SpatialParams p) {
       if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = acc;
       else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(acc);
     }
+  }
+}
+
+// The bandwidth kernel of the spatial pyramid (175 616 elements read per frame, 896 written).  The
+// [frames * C, HW] map is a flat stream of short rows (HW = 784 / 196 / 49: 3136 / 784 / 196 bytes in fp32, the last
+// not even 16-byte aligned per row), so instead of shaping the loads around rows, persistent CTAs pull TILES of whole
+// rows (<= kSpatialTileBytes, a multiple of 16 bytes by construction) into a 3-slot shared-memory ring with
+// cp.async.bulk (one thread issues, mbarrier complete_tx; bytes in flight do not depend on registers or on the warps'
+// instruction streams) and reduce the rows out of shared memory: a warp per row for long rows, a LANE per row when
+// HW is short and odd (lane stride HW words is then conflict-free) so no lane idles on 49-element rows.
+constexpr int kSpatialTileBytes = 24 * 1024, kSpatialStages = 3, kSpatialThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kSpatialThreads) spatial_tile_kernel(const SpatialParams p) {
+  extern __shared__ __align__(128) unsigned char sp_smem[];
+  __shared__ __align__(8) uint64_t full_bar[kSpatialStages];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long rows = p.frames * p.C, R = p.rows_per_tile;
+  const int hw = static_cast<int>(p.hw);
+  const float inv = 1.0f / static_cast<float>(hw);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kSpatialStages; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const unsigned char* gx = reinterpret_cast<const unsigned char*>(p.x);
+  auto issue = [&](int slot, long long tile) {
+    const long long r0 = tile * R;
+    const long long nr = rows - r0 < R ? rows - r0 : R;
+    const uint32_t bytes = static_cast<uint32_t>(nr * hw * static_cast<long long>(sizeof(T)));   // host: every tile a multiple of 16
+    const uint32_t bar = smem_u32(&full_bar[slot]);
+    mbar_arrive_expect_tx(bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sp_smem + slot * kSpatialTileBytes)), "l"(gx + r0 * hw * static_cast<long long>(sizeof(T))), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kSpatialStages; ++s) {
+      const long long t = blockIdx.x + static_cast<long long>(s) * gridDim.x;
+      if (t < p.ntiles) issue(s, t);
+    }
+  }
+  const bool lane_rows = hw < 64 && (hw & 1);
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int slot = it % kSpatialStages;
+    mbar_wait(smem_u32(&full_bar[slot]), (it / kSpatialStages) & 1);
+    const T* t = reinterpret_cast<const T*>(sp_smem + slot * kSpatialTileBytes);
+    const long long r0 = tile * R;
+    const int nr = static_cast<int>(rows - r0 < R ? rows - r0 : R);
+    auto emit = [&](int r, float acc) {
+      const long long fc = r0 + r, f = fc / p.C, c = fc - f * p.C;
+      const long long o = f * p.ld_out + p.col_off + c;
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = acc * inv;
+      else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(acc * inv);
+    };
+    if (lane_rows) {
+      for (int r = tid; r < nr; r += kSpatialThreads) {
+        const T* row = t + r * hw;
+        float a0 = 0.0f, a1 = 0.0f;
+        int i = 0;
+        for (; i + 1 < hw; i += 2) { a0 += Elem<T>::to_f(row[i]); a1 += Elem<T>::to_f(row[i + 1]); }
+        if (i < hw) a0 += Elem<T>::to_f(row[i]);
+        emit(r, a0 + a1);
+      }
+    } else {
+      for (int r = warp; r < nr; r += kSpatialThreads / 32) {
+        const T* row = t + r * hw;
+        float a0 = 0.0f, a1 = 0.0f;
+        int i = lane;
+        for (; i + 32 < hw; i += 64) { a0 += Elem<T>::to_f(row[i]); a1 += Elem<T>::to_f(row[i + 32]); }
+        if (i < hw) a0 += Elem<T>::to_f(row[i]);
+        const float acc = warp_sum(a0 + a1);
+        if (lane == 0) emit(r, acc);
+      }
+    }
+    __syncthreads();                       // every warp is done with the slot
+    const long long next = tile + static_cast<long long>(kSpatialStages) * gridDim.x;
+    if (tid == 0 && next < p.ntiles) {
+      fence_proxy_async_smem();            // generic-proxy reads of the slot before the async-proxy refill
+      issue(slot, next);
+    }
+  }
+}
+
+// Backward of the average pool: dx[f, c, :] = dpooled[f, col_off + c] / HW — a pure write stream.  A CTA owns a
+// contiguous chunk of rows whose start is 16-byte aligned (host), stages the chunk's pooled gradients in shared memory
+// and writes 16-byte vectors; the row of a vector's first element is one 32-bit division, its neighbours step from it.
+struct SpatialBwdParams { const float* dpooled; void* dx; long long frames, C, hw, ld, col_off, rows_per_chunk, nchunks; };
+constexpr int kSpatialBwdRows = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(256) spatial_bwd_kernel(const SpatialBwdParams p) {
+  constexpr int V = Vec16<T>::kN;
+  __shared__ float g[kSpatialBwdRows];
+  const long long rows = p.frames * p.C;
+  const uint32_t hw = static_cast<uint32_t>(p.hw);
+  const float inv = 1.0f / static_cast<float>(hw);
+  for (long long chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x) {
+    const long long r0 = chunk * p.rows_per_chunk;
+    const int nr = static_cast<int>(rows - r0 < p.rows_per_chunk ? rows - r0 : p.rows_per_chunk);
+    __syncthreads();
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+      const long long fc = r0 + r, f = fc / p.C, c = fc - f * p.C;
+      g[r] = p.dpooled[f * p.ld + p.col_off + c] * inv;
+    }
+    __syncthreads();
+    const uint32_t elems = static_cast<uint32_t>(nr) * hw;
+    T* dst = reinterpret_cast<T*>(p.dx) + r0 * p.hw;
+    const uint32_t nvec = elems / V;
+    for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const uint32_t e = v * V;
+      uint32_t r = e / hw, rem = e - r * hw;
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        o[i] = g[r];
+        if (++rem == hw) { rem = 0; ++r; }
+      }
+      Vec16<T>::store(dst + e, o);
+    }
+    for (uint32_t e = nvec * V + threadIdx.x; e < elems; e += blockDim.x) dst[e] = Elem<T>::from_f(g[e / hw]);   // < V tail elements
   }
 }
 
@@ -201,10 +329,59 @@ extern "C" int tvt_spatial_pool_fwd(const tvt_spatial_pool_args* a, void* stream
   TVT_REQUIRE((a->dtype == TVT_BF16 || a->dtype == TVT_F32) && (a->out_dtype == TVT_BF16 || a->out_dtype == TVT_F32), "tvt_spatial_pool_fwd: bad dtype");
   int rc = require_sm100();
   if (rc != TVT_OK) return rc;
-  pool::SpatialParams p{a->x, a->out, a->frames, a->channels, a->hw, a->ld_out, a->col_offset, a->out_dtype == TVT_F32};
-  const long long warps = a->frames * a->channels;
+  pool::SpatialParams p{a->x, a->out, a->frames, a->channels, a->hw, a->ld_out, a->col_offset, a->out_dtype == TVT_F32, 0, 0};
+  const long long rows = a->frames * a->channels;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->dtype == TVT_F32) pool::spatial_kernel<float><<<pool::grid_for(warps * 32, 256), 256, 0, s>>>(p);
-  else pool::spatial_kernel<__nv_bfloat16><<<pool::grid_for(warps * 32, 256), 256, 0, s>>>(p);
+  // tile = the largest multiple of r0 rows within kSpatialTileBytes, r0 = rows per 16-byte period of the row pitch
+  const long long row_bytes = a->hw * (a->dtype == TVT_F32 ? 4 : 2);
+  long long gcd = row_bytes, y = 16;
+  while (y) { const long long t = gcd % y; gcd = y; y = t; }
+  const long long r0 = 16 / gcd;
+  long long R = (pool::kSpatialTileBytes / (r0 * row_bytes)) * r0;
+  // the final (partial) tile must also be a whole number of 16-byte units: true when rows % r0 == 0
+  if (R > 0 && al16(a->x) && rows % r0 == 0 && a->hw < (1 << 20)) {
+    if (R >= 16) R -= R % 8;                                     // whole rounds of the 8 warps
+    p.rows_per_tile = R;
+    p.ntiles = (rows + R - 1) / R;
+    static bool attr_set = false;
+    const int smem = pool::kSpatialStages * pool::kSpatialTileBytes;
+    if (!attr_set) {
+      cudaFuncSetAttribute(pool::spatial_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(pool::spatial_tile_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_set = true;
+    }
+    const long long cap = static_cast<long long>(num_sms()) * 3;   // 72 KB per CTA: three resident per SM
+    const int grid = static_cast<int>(p.ntiles < cap ? p.ntiles : cap);
+    if (a->dtype == TVT_F32) pool::spatial_tile_kernel<float><<<grid, pool::kSpatialThreads, smem, s>>>(p);
+    else pool::spatial_tile_kernel<__nv_bfloat16><<<grid, pool::kSpatialThreads, smem, s>>>(p);
+    return check_launch("tvt_spatial_pool_fwd");
+  }
+  if (a->dtype == TVT_F32) pool::spatial_kernel<float><<<pool::grid_for(rows * 32, 256), 256, 0, s>>>(p);
+  else pool::spatial_kernel<__nv_bfloat16><<<pool::grid_for(rows * 32, 256), 256, 0, s>>>(p);
   return check_launch("tvt_spatial_pool_fwd");
+}
+
+extern "C" int tvt_spatial_pool_bwd(const tvt_spatial_pool_bwd_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->dpooled && a->dx, "tvt_spatial_pool_bwd: null pointer");
+  TVT_REQUIRE(a->frames > 0 && a->channels > 0 && a->hw > 0 && a->hw < (1 << 20), "tvt_spatial_pool_bwd: bad shape");
+  TVT_REQUIRE(a->ld >= a->col_offset + a->channels, "tvt_spatial_pool_bwd: ld too small");
+  TVT_REQUIRE(a->dtype == TVT_BF16 || a->dtype == TVT_F32, "tvt_spatial_pool_bwd: bad dtype");
+  TVT_REQUIRE(al16(a->dx), "tvt_spatial_pool_bwd: dx must be 16-byte aligned");
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  const long long rows = a->frames * a->channels;
+  const long long row_bytes = a->hw * (a->dtype == TVT_F32 ? 4 : 2);
+  long long gcd = row_bytes, y = 16;
+  while (y) { const long long t = gcd % y; gcd = y; y = t; }
+  const long long r0 = 16 / gcd;                                  // chunk starts stay 16-byte aligned
+  long long R = (pool::kSpatialBwdRows / r0) * r0;
+  while (R > r0 && R * a->hw > (1LL << 16)) R -= r0;              // ~64 Ki elements per chunk
+  pool::SpatialBwdParams p{static_cast<const float*>(a->dpooled), a->dx, a->frames, a->channels, a->hw, a->ld, a->col_offset, R, (rows + R - 1) / R};
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  const int grid = static_cast<int>(p.nchunks < cap ? p.nchunks : cap);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->dtype == TVT_F32) pool::spatial_bwd_kernel<float><<<grid, 256, 0, s>>>(p);
+  else pool::spatial_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
+  return check_launch("tvt_spatial_pool_bwd");
 }

@@ -28,7 +28,21 @@ def direct_target(p):
     pr, rr = ent[0](), ent[1]()
     if pr is not p or rr is None or p.grad is None:
         return None
-    return p.grad, (lambda: rr._on_grad(p))
+    return p.grad, (lambda: rr._on_direct(p))
+
+
+def note_use(p):
+    """Called by an autograd Function's FORWARD for every parameter whose gradient its backward will write through a
+    direct sink: the reducer counts the uses, and a parameter only counts as complete once every use has reported
+    ``done()``.  A module applied several times per step (``SimpleTransformer.ptn_shared`` runs ``transformer_encoder0``
+    once per expert, src/models/transformer.py:84-104) would otherwise arm its bucket's all-reduce on the FIRST
+    contribution while later ones are still accumulating into the same flat buffer."""
+    ent = _DIRECT.get(id(p))
+    if ent is None:
+        return
+    pr, rr = ent[0](), ent[1]()
+    if pr is p and rr is not None:
+        rr._uses[id(p)] = rr._uses.get(id(p), 0) + 1
 
 
 class GradBucketReducer:
@@ -39,6 +53,7 @@ class GradBucketReducer:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.buckets = []          # list of dict(flat, params, pending, handle)
         self._index = {}
+        self._uses = {}            # id(param) -> direct-sink uses registered by forward and not yet reported done
         cur, cur_bytes = [], 0
         for p in reversed(self.params):                      # backward order
             cur.append(p)
@@ -78,10 +93,18 @@ class GradBucketReducer:
             b["pending"] = len(b["params"])
             b["handle"] = None
             b["seen"].clear()
+        self._uses.clear()
+
+    def _on_direct(self, p):
+        """One direct-sink use of ``p`` has issued its kernels; the parameter completes when all registered uses have."""
+        left = self._uses.get(id(p), 1) - 1
+        self._uses[id(p)] = max(left, 0)
+        if left <= 0:
+            self._on_grad(p)
 
     def _on_grad(self, p):
         b = self._index[id(p)]
-        if id(p) in b["seen"]:          # a second contribution to the same parameter in one backward: counted once
+        if id(p) in b["seen"]:          # a further backward without zero_grad(): the bucket is already accounted for
             return
         b["seen"].add(id(p))
         b["pending"] -= 1

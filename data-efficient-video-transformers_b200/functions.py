@@ -11,6 +11,7 @@ with a hand-scheduled backward (fused epilogues, recomputed dropout masks, no te
   ReadoutFn       CLS gather (+ expert sum) and sum_group     src/models/transformer.py:123-130, TPN.py:64-72
   DistillLossFn   BCE + CE(argmax teacher) + KL               src/models/frame_transformer.py:250-257
   PyramidHeadFn   sigmoid, mean over scales, BCE              src/models/TPN.py:98,112
+  SpatialPoolFn   AvgPool2d to 1x1 of a CNN feature map       src/models/TPN.py:5,19,32
 
 Tokens are kept batch-major inside the package: a (B, S, d) sequence batch is a [B*S, d] matrix.
 """
@@ -61,6 +62,14 @@ class _Sink:
         return self.buf
 
 
+def _note_uses(ctx, params, first):
+    """Forward-side registration of the parameters this Function's backward will write through ``_Sink``s (see
+    ``ddp.note_use``); ``first`` = position of ``params[0]`` among forward's arguments."""
+    for i, p in enumerate(params):
+        if p is not None and ctx.needs_input_grad[first + i]:
+            ddp.note_use(p)
+
+
 class LayerCfg:
     """Static description of one attention block call."""
 
@@ -108,6 +117,7 @@ class EncoderLayerFn(torch.autograd.Function):
         ctx.cfg, ctx.seeds, ctx.dims = cfg, seeds, (n, d, B, H, hd, Sq, Sk, ff)
         ctx.cross = mem is not None
         ctx.params = (in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b)   # gradient sinks (leaf parameters)
+        _note_uses(ctx, ctx.params, 3)
         ctx.save_for_backward(x, mem, qkv, kv, attn, lse, y1, mean1, rstd1, x1, h, z, y2, mean2, rstd2,
                               in_w, out_w, l1_w, l2_w, n1_w, n2_w)
         return out
@@ -270,6 +280,12 @@ class EmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mode, feat, cls, pe, norm_w, norm_b, p):
         B, T, d = feat.shape
+        # the kernel cannot know the buffers' lengths: refuse here what the reference refuses with a torch.cat / broadcast
+        # error (a batch larger than hparams.batch_size CLS slots, a sequence longer than PositionalEncoding's max_len)
+        if cls.numel() % d != 0 or B > cls.numel() // d:
+            raise ValueError(f"embed: batch of {B} clips but the CLS parameter {tuple(cls.shape)} holds {cls.numel() // d} batch slots")
+        if pe.numel() % d != 0 or T + 1 > pe.numel() // d:
+            raise ValueError(f"embed: sequence of {T} + 1 tokens exceeds PositionalEncoding max_len {pe.numel() // d}")
         seed = next_seed() if p > 0 else 0
         cls_act = cls.detach().reshape(-1, d)[:B].to(mode.dtype).contiguous()
         pe2 = pe.reshape(-1, d)[: T + 1].contiguous()
@@ -316,6 +332,7 @@ class LinearFn(torch.autograd.Function):
         y = mode.linear_fwd(xp, M, K, w, b)
         ctx.mode = mode
         ctx.params = (w, b)
+        _note_uses(ctx, ctx.params, 2)
         ctx.save_for_backward(x, w)
         return y
 
@@ -376,6 +393,7 @@ class MlpFn(torch.autograd.Function):
         ctx.mode, ctx.acts, ctx.drops, ctx.seeds, ctx.nl = mode, acts, drops, seeds, nl
         ctx.save_for_backward(x, *ys, *[z if z is not None else x.new_empty(0) for z in zs], *ws)
         ctx.params = (ws, bs)
+        _note_uses(ctx, wb, 4)
         return cur
 
     @staticmethod
@@ -513,3 +531,23 @@ class PyramidHeadFn(torch.autograd.Function):
     def backward(ctx, _dprob, dloss):
         (dz,) = ctx.saved_tensors
         return dz * dloss, None
+
+
+class SpatialPoolFn(torch.autograd.Function):
+    """maps [frames, C, H, W] (fp32 or bf16) -> pooled [frames, C] fp32 = mean over H*W (nn.AvgPool2d(kernel_size=H) on an
+    H x H map, src/models/TPN.py:5,19,32); backward broadcasts dpooled / (H*W) over the map."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        out = torch.empty(x.shape[0], x.shape[1], dtype=torch.float32, device=x.device)
+        ops.spatial_pool(x, out, 0)
+        ctx.meta = (tuple(x.shape), x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        shape, dtype = ctx.meta
+        dx = torch.empty(shape, dtype=dtype, device=dpooled.device)
+        ops.spatial_pool_bwd(dpooled.contiguous().float(), dx, 0)
+        return dx

@@ -1,13 +1,13 @@
-"""Drop-in for the reference's src/models/TPN.py pyramid parts: ``sum_group`` (:64-72), ``Reasoning``
-(:75-112) and the spatial pyramid (:2-40, concat order high, mid, low :58).  The ResNet-34 trunk that
-produces the feature maps (TPN.net) is out of scope."""
+"""Drop-in for the reference's src/models/TPN.py: ``sum_group`` (:64-72), ``Reasoning`` (:75-112), the spatial
+pyramid ``Feature_Pyramid_low / Mid / High`` (:2-40, trainable 1x1 convs, concat order high, mid, low :58) and ``TPN``
+(:43-61).  The ResNet-34 trunk that produces the feature maps (TPN.net) is a library plug-in (out of scope as a kernel)."""
 import torch
 import torch.nn as nn
 
 from .. import ops
 from ..capi import ACT_RELU
 from ..compat import LightningModule
-from ..functions import HeadLinearFn, MlpFn, PyramidHeadFn, ReadoutFn
+from ..functions import HeadLinearFn, LinearFn, MlpFn, PyramidHeadFn, ReadoutFn, SpatialPoolFn
 from .common import to_act
 
 
@@ -92,32 +92,102 @@ class _PoolAll(torch.autograd.Function):
         return None, None, None, dx
 
 
-class SpatialPyramid(nn.Module):
-    """Feature_Pyramid_low / Mid / High + concat (TPN.py:2-40,55-58): avg-pool each map to 1x1 (bandwidth
-    kernel), 1x1 conv on low and mid (a [C, C] GEMM on the pooled vectors), High pooled only; output
-    (frames, 896) in the order (high, mid, low).  Inference path (the maps come from a frozen CNN)."""
+class _FeaturePyramid(nn.Module):
+    """Feature_Pyramid_low / Mid / High (TPN.py:2-40): ``pool_branch`` = AvgPool2d(k) of a k x k map, ``channels_reduce`` =
+    a trainable 1x1 conv = a [C, C] Linear on the pooled vector.  The pool is the bandwidth kernel (``SpatialPoolFn``:
+    TMA-bulk tile ring, forward and backward), the conv a tensor-core GEMM (``LinearFn``: bias epilogue, wgrad / dgrad /
+    bias-gradient backward), so the module trains like the reference's.  forward returns [frames, C, 1, 1] like the
+    reference (TPN.forward squeezes it)."""
 
-    def __init__(self):
+    C, K, USE_CONV = 0, 0, True
+
+    def __init__(self, precision="fp32"):
         super().__init__()
-        self.pyramid_low = nn.ModuleDict({"channels_reduce": nn.Conv2d(128, 128, kernel_size=1)})
-        self.pyramid_mid = nn.ModuleDict({"channels_reduce": nn.Conv2d(256, 256, kernel_size=1)})
-        self.pyramid_high = nn.ModuleDict({"channels_reduce": nn.Conv2d(512, 512, kernel_size=1)})
-        self.mode = ops.Mode("fp32")
+        self.pool_branch = nn.Sequential(nn.AvgPool2d(kernel_size=self.K))
+        self.channels_reduce = nn.Conv2d(self.C, self.C, kernel_size=1)
+        self.mode = ops.Mode(precision)
 
-    @torch.no_grad()
+    def pooled(self, x):
+        """[frames, C, K, K] -> [frames, C] (after the 1x1 conv when the level has one) in the mode's dtype."""
+        if not x.is_cuda:
+            raise ops.TvtError("input tensor is not on a CUDA device: this path has no CPU implementation")
+        if x.shape[1] != self.C or x.shape[2] != self.K or x.shape[3] != self.K:
+            raise ValueError(f"{type(self).__name__}: expected a [*, {self.C}, {self.K}, {self.K}] map, got {tuple(x.shape)}")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        p = SpatialPoolFn.apply(x)
+        if not self.USE_CONV:
+            return p
+        p = p if self.mode.fp32 else p.to(torch.bfloat16)
+        w = self.channels_reduce.weight
+        return LinearFn.apply(self.mode, p, w.view(self.C, self.C), self.channels_reduce.bias).float()
+
+    def forward(self, x):
+        return self.pooled(x).view(-1, self.C, 1, 1)
+
+
+class Feature_Pyramid_Mid(_FeaturePyramid):
+    C, K = 256, 14
+
+
+class Feature_Pyramid_High(_FeaturePyramid):
+    """TPN.py:16-26: the High level constructs its conv but returns the pooled tensor without applying it."""
+    C, K, USE_CONV = 512, 7, False
+
+
+class Feature_Pyramid_low(_FeaturePyramid):
+    C, K = 128, 28
+
+
+class ResNetMaps(nn.Module):
+    """The (layer2, layer3, layer4) feature maps of a torchvision ResNet — what the reference's
+    ``custom_resnet.ResNet.forward`` returns (custom_resnet.py:138-153).  Library CNN, out of scope as a kernel."""
+
+    def __init__(self, arch="resnet34", pretrained=False):
+        super().__init__()
+        import torchvision.models as models
+        net = getattr(models, arch)(weights="DEFAULT" if pretrained else None)
+        for name in ("conv1", "bn1", "relu", "maxpool", "layer1", "layer2", "layer3", "layer4", "avgpool", "fc"):
+            setattr(self, name, getattr(net, name))
+
+    def forward(self, x):
+        x = self.layer1(self.maxpool(self.relu(self.bn1(self.conv1(x)))))
+        x2 = self.layer2(x)
+        x3 = self.layer3(x2)
+        return x2, x3, self.layer4(x3)
+
+
+class TPN(LightningModule):
+    """TPN.py:43-61: CNN trunk -> spatial pyramid (low / mid / high, concat order high, mid, low -> 896) -> ``Reasoning``
+    over the frames.  ``net`` is a plug-in returning the three maps (default: torchvision's ResNet-34, no download)."""
+
+    def __init__(self, net=None, precision="fp32", pretrained=False):
+        super().__init__()
+        self.net = net if net is not None else ResNetMaps("resnet34", pretrained)
+        self.pyramid_low = Feature_Pyramid_low(precision)
+        self.pyramid_mid = Feature_Pyramid_Mid(precision)
+        self.pyramid_high = Feature_Pyramid_High(precision)
+        self.reason = Reasoning(precision=precision)
+
+    def frame_features(self, low, mid, high):
+        """The three maps of N frames -> [N, 896] in the reference's concat order (TPN.py:55-58)."""
+        return torch.cat((self.pyramid_high.pooled(high), self.pyramid_mid.pooled(mid), self.pyramid_low.pooled(low)), dim=-1)
+
+    def forward(self, x):
+        low, mid, high = self.net(x)
+        cnn_out = self.frame_features(low, mid, high).unsqueeze(0)        # TPN.py:58: one clip of N frames
+        return self.reason(cnn_out)
+
+
+class SpatialPyramid(nn.Module):
+    """The three pyramid levels + concat as one module (``TPN`` without its CNN and Reasoning): maps -> (frames, 896) in
+    the order (high, mid, low).  Submodule / parameter names are TPN's (pyramid_low.channels_reduce.weight ...)."""
+
+    def __init__(self, precision="fp32"):
+        super().__init__()
+        self.pyramid_low = Feature_Pyramid_low(precision)
+        self.pyramid_mid = Feature_Pyramid_Mid(precision)
+        self.pyramid_high = Feature_Pyramid_High(precision)
+
     def forward(self, low, mid, high):
-        frames = low.shape[0]
-        out = torch.empty(frames, 896, dtype=torch.float32, device=low.device)
-        pooled_mid = torch.empty(frames, 256, dtype=torch.float32, device=low.device)
-        pooled_low = torch.empty(frames, 128, dtype=torch.float32, device=low.device)
-        ops.spatial_pool(high.contiguous(), out, 0)
-        ops.spatial_pool(mid.contiguous(), pooled_mid, 0)
-        ops.spatial_pool(low.contiguous(), pooled_low, 0)
-        for pooled, conv, off in ((pooled_mid, self.pyramid_mid["channels_reduce"], 512),
-                                  (pooled_low, self.pyramid_low["channels_reduce"], 768)):
-            Cc = pooled.shape[1]
-            w = conv.weight.view(Cc, Cc)
-            wh, wl = self.mode.weight(w)
-            xp = self.mode.split(pooled)
-            ops.gemm(xp[0], wh, frames, Cc, Cc, a_lo=xp[1], b_lo=wl, bias=conv.bias, out_f32=out[:, off:off + Cc])
-        return out
+        return torch.cat((self.pyramid_high.pooled(high), self.pyramid_mid.pooled(mid), self.pyramid_low.pooled(low)), dim=-1)

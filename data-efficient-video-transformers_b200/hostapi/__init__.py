@@ -2,8 +2,9 @@
 arguments, forward signatures, Lightning hook names and state_dict keys; the arithmetic underneath runs
 on the package's sm_100a kernels through torch.autograd.Functions (see ..functions)."""
 from .transformer import PositionalEncoding, SimpleTransformer  # noqa: F401
-from .frame_transformer import TransformerBase, FrameStream  # noqa: F401
-from .TPN import Reasoning, sum_group, SpatialPyramid  # noqa: F401
+from .frame_transformer import TransformerBase, FrameStream, FrameTransformer, ImgResNet, VidResNet  # noqa: F401
+from .TPN import (Reasoning, sum_group, SpatialPyramid, Feature_Pyramid_low, Feature_Pyramid_Mid,  # noqa: F401
+                  Feature_Pyramid_High, TPN, ResNetMaps)
 from .fusion import CrossModalBlock, ExpertStream, FusionTransformer, DistillationTrainer  # noqa: F401
 from .inference import EvalBuffer, GraphedForward, REFERENCE_THRESHOLDS  # noqa: F401
 from .collabgating import CollaborativeGating  # noqa: F401

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..capi import ACT_GELU, ACT_NONE
+from ..capi import ACT_GELU, ACT_NONE, TvtError
 from ..compat import LightningModule
 from ..functions import DistillLossFn, HeadLinearFn, MlpFn, ReadoutFn
 from .common import make_encoder, run_encoder, to_act
@@ -86,3 +86,235 @@ class FrameStream(LightningModule):
             self.log("train/cossim", losses[4])
         self.log("train/loss", losses[0])
         return losses[0]
+
+
+# ------------------------------------------------------------------------------------------ the two-stream model
+def _torchvision_backbone(kind, pretrained):
+    """The CNN backbones are OUT OF SCOPE as kernels — they are library modules plugged into the
+    drop-in class: torchvision's own R(2+1)D-18 / ResNet-18, constructed without a download unless asked."""
+    import torchvision.models as models
+    if kind == "vid":
+        return models.video.r2plus1d_18(weights="DEFAULT" if pretrained else None)
+    return models.resnet18(weights="DEFAULT" if pretrained else None)
+
+
+class ImgResNet(LightningModule):
+    """frame_transformer.py:50-61: ResNet-18 with a Linear(512, 896) head, run under no_grad (frozen)."""
+
+    def __init__(self, pretrained=False, out_dim=896):
+        super().__init__()
+        self.backbone = _torchvision_backbone("img", pretrained)
+        self.backbone.fc = nn.Sequential(nn.Linear(self.backbone.fc.in_features, out_dim))
+
+    def forward(self, x):
+        with torch.no_grad():
+            return self.backbone(x)
+
+
+class VidResNet(LightningModule):
+    """frame_transformer.py:64-74: R(2+1)D-18 with a Linear(512, 896) head, trainable."""
+
+    def __init__(self, pretrained=False, out_dim=896):
+        super().__init__()
+        self.backbone = _torchvision_backbone("vid", pretrained)
+        self.backbone.fc = nn.Sequential(nn.Linear(self.backbone.fc.in_features, out_dim))
+
+    def forward(self, x):
+        return self.backbone(x)
+
+
+class FrameTransformer(LightningModule):
+    """Drop-in for src/models/frame_transformer.py:83-367: ``FrameTransformer(**config)`` with every ``config.yaml`` key,
+    ``forward(img, vid)``, ``training_step / validation_step / test_step``, ``configure_optimizers`` by ``hparams.opt``,
+    the ``running_logits / running_labels`` side channel of the callbacks, and the reference's ``state_dict`` keys.
+
+    Everything after the CNN backbones — CLS concat, ``view(batch_size, S, 896)``, PositionalEncoding, the 4-layer
+    TransformerBase encoders (d = 896: 2 heads of 448 for the video stream, 4 heads of 224 for the image stream), CLS
+    read-out, the GELU MLP head and the losses — runs on this package's sm_100a kernels through autograd Functions.  The
+    backbones are plug-ins: by default torchvision's own R(2+1)D-18 / ResNet-18 (``pretrained=False`` unless the
+    ``pretrained`` key says otherwise; the reference asks for downloaded weights), or any module passed as
+    ``vid_model=`` / ``img_model=``, or the string ``"features"`` = FEATURE MODE, where ``vid`` / ``img`` already are
+    (B, S - 1, 896) backbone features (what BASELINE.json's synthetic configs feed) and ``vid_cls`` / ``img_cls`` are
+    (1, 896) rows.
+
+    Modes (``hparams.model``; main.py:43 accepts frame_transformer, distil, sum, frame, vid, pre_modal, sum_residual).
+    Only "vid" runs in the reference at this commit; the others are built the way ``oracle.param.FrameTransformer``
+    documents restoration by restoration (the three commented constructor lines :94,98,104 re-enabled — only for the
+    modes that need them, so the "vid" ``state_dict`` stays the reference's —, ``unsqueeze`` on the injected token,
+    the head applied to both vectors in "distil", "pre_modal" == "frame" as executed, "sum_residual" as written).
+    Extra optional keys: ``precision`` ("bf16" | "fp32"), ``pretrained``, ``vid_model``, ``img_model``, ``feature_dim``."""
+
+    D = 896          # frame_transformer.py:91,99,106 hard-code the width
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        vid_model = kwargs.pop("vid_model", None)
+        img_model = kwargs.pop("img_model", None)
+        self.save_hyperparameters()
+        hp = self.hparams
+        hp.setdefault("model", "vid")
+        hp.setdefault("cls", 1)
+        hp.setdefault("seq_len", 13)
+        hp.setdefault("batch_size", 2)
+        hp.setdefault("precision", "bf16")
+        hp.setdefault("pretrained", False)
+        if hp.cls:
+            hp.seq_len += 1
+        d = int(hp.get("feature_dim", self.D))
+        self.d = d
+        self.mode = ops.Mode(hp.precision)
+        n_classes = 19                                                  # :106 (config.yaml's n_classes is not read there)
+        self.criterion = nn.BCEWithLogitsLoss()
+        self.distil_criterion = nn.CrossEntropyLoss()
+        extra = 1 if hp.model == "sum" else 0                           # the injected token (see class docstring)
+        self.position_encoder = PositionalEncoding(d, 0.5, max_len=14 + extra)
+        self.feature_mode_vid = isinstance(vid_model, str) and vid_model == "features"
+        self.vid_model = None if self.feature_mode_vid else (vid_model if vid_model is not None else VidResNet(hp.pretrained, d))
+        self.distil_transformer = TransformerBase(d, 128, 2, 512, 4, 0.5, hp.precision)
+        self.distil_transformer.mode = self.mode
+        self.running_labels, self.running_logits, self.running_paths, self.running_embeds = [], [], [], []
+        self.vid_cls = nn.Parameter(torch.rand(1, d) if self.feature_mode_vid else torch.rand(1, 12, 3, 112, 112))
+        self.img_mlp_head = nn.Sequential(nn.Linear(d, 512), nn.GELU(), nn.Linear(512, 128), nn.GELU(), nn.Linear(128, n_classes))
+        from ..compat import AveragePrecision
+        self.train_aprc = AveragePrecision(num_classes=19)
+        self.norm = nn.LayerNorm(d)
+        self.val_aprc = AveragePrecision(num_classes=19)
+        self.cos = nn.CosineSimilarity(dim=1)
+        if hp.model != "vid":                                           # :94,98,104 restored for the modes that use them
+            self.feature_mode_img = isinstance(img_model, str) and img_model == "features"
+            self.img_model = None if self.feature_mode_img else (img_model if img_model is not None else ImgResNet(hp.pretrained, d))
+            self.scene_transformer = TransformerBase(d, d, 4, d, 4, 0.5, hp.precision)
+            self.scene_transformer.mode = self.mode
+            self.img_cls = nn.Parameter(torch.rand(1, d) if self.feature_mode_img else torch.rand(1, 3, 224, 224))
+
+    def configure_optimizers(self):
+        """frame_transformer.py:123-134 (an unknown ``opt`` is an UnboundLocalError there; a ValueError here)."""
+        hp = self.hparams
+        if hp.opt == "sgd":
+            return torch.optim.SGD(self.parameters(), lr=hp.learning_rate, momentum=hp.momentum, weight_decay=hp.weight_decay)
+        if hp.opt == "adamW":
+            return torch.optim.AdamW(self.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
+        if hp.opt == "adagrad":
+            return torch.optim.Adagrad(self.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
+        raise ValueError(f"opt must be 'sgd', 'adamW' or 'adagrad', got {hp.opt!r}")
+
+    # ---- the feature-sequence path on the sm_100a kernels
+    def _features(self, cls, data, backbone, video):
+        """Per-clip CLS concat + backbone (:193-204, :213-222) -> (B, S, d) features."""
+        total = [torch.cat((cls, data[i]), dim=0) for i in range(len(data))]
+        x = torch.stack(total)
+        if backbone is not None:
+            x = x.view(-1, *x.shape[2:])
+            x = backbone(x.permute(0, 2, 1, 3, 4) if video else x)
+        S = 14 if video else self.hparams.seq_len
+        return x.reshape(self.hparams.batch_size, S, self.d)
+
+    def _act(self, x):
+        """Backbone features -> the mode's activation dtype, keeping the autograd edge into a trainable backbone."""
+        if not x.is_cuda:
+            raise TvtError("input tensor is not on a CUDA device: this path has no CPU implementation")
+        if x.requires_grad:
+            return x.float().contiguous() if self.mode.fp32 else x.to(torch.bfloat16).contiguous()
+        return to_act(self.mode, x)
+
+    def _encode(self, feats, transformer, inject=None):
+        """(B, S, d) -> encoded (B, S[+1], d): PositionalEncoding (+dropout) then the encoder stack."""
+        B, S, d = feats.shape
+        x = self._act(feats)
+        if inject is not None:
+            x = torch.cat((x, inject.to(x.dtype).unsqueeze(1)), dim=1).contiguous()
+            S += 1
+        tok = self.position_encoder.tokens_forward(x.view(B * S, d), S)
+        return transformer.tokens_forward(tok, B).view(B, S, d)
+
+    def _head(self, cls):
+        h = self.img_mlp_head
+        y = MlpFn.apply(self.mode, (ACT_GELU, ACT_GELU), (0.0, 0.0), cls.contiguous(), h[0].weight, h[2].weight, h[0].bias, h[2].bias)
+        return HeadLinearFn.apply(y, h[4].weight, h[4].bias)
+
+    def vid_step(self, data):
+        """:192-210 -> the video stream's CLS vector (B, d)."""
+        feats = self._features(self.vid_cls, data, self.vid_model, video=not self.feature_mode_vid)
+        seq = self._encode(feats, self.distil_transformer)
+        return seq[:, 0]
+
+    def img_step(self, data, distil_inject):
+        """:212-244."""
+        m = self.hparams.model
+        feats = self._features(self.img_cls, data, self.img_model, video=False)
+        seq = self._encode(feats, self.scene_transformer, inject=distil_inject if m == "sum" else None)
+        cls = seq[:, 0]
+        if m in ("distil", "sum"):
+            return cls, seq[:, -1]
+        if m == "sum_residual":
+            return cls, seq
+        return self._head(cls)
+
+    def distillation_step(self, img, vid):
+        vid_cls = self.vid_step(vid)
+        return self.img_step(img, vid_cls)
+
+    def pre_modal(self, img, vid):
+        return self.img_step(img, None)          # :187-190 as executed (see class docstring)
+
+    def forward(self, img, vid):
+        m = self.hparams.model
+        if m == "distil":
+            vid_cls = self.vid_step(vid)
+            img_cls, _ = self.img_step(img, vid_cls)
+            return self._head(img_cls), self._head(vid_cls)
+        if m == "sum":
+            img_cls, vid_tkn = self.distillation_step(img, vid)
+            return self._head(img_cls + vid_tkn)
+        if m == "sum_residual":
+            self.vid_step(vid)
+            img_cls, _ = self.img_step(img, None)
+            a = torch.nn.functional.normalize(img_cls.float(), p=2.0, dim=-1)
+            b = torch.nn.functional.normalize(a, p=2.0, dim=-1)
+            return self._head((a + b).to(self.mode.dtype))
+        if m in ("frame", "pre_modal"):
+            return self.img_step(img, None)
+        if m == "vid":
+            return self._head(self.vid_step(vid))
+        return None                               # "frame_transformer" has no branch in the reference's forward either
+
+    # ---- Lightning hooks
+    def _loss_and_logits(self, batch, stage):
+        m = self.hparams.model
+        target, img, vid = batch[0], batch[1], batch[2]
+        target = target.reshape(-1, target.shape[-1]).float()
+        if m == "distil":
+            s, t = self(img, vid)
+            losses = DistillLossFn.apply(s, t.detach(), target, 1.0, 1.0, 0.0, 1.0)
+            self.log(f"{stage}/distilloss", losses[2], on_step=True, on_epoch=True)
+            self.log(f"{stage}/bass_loss" if stage == "train" else f"{stage}/base_loss", losses[1], on_step=True, on_epoch=True)
+            self.log(f"{stage}/cossim", losses[4], on_step=True, on_epoch=True)
+            return losses[0], s, target
+        data = self(img if m != "vid" else None, vid if m != "frame" else None)
+        if data is None:
+            raise ValueError(f"model={m!r} has no forward branch (frame_transformer.py:136-180)")
+        return DistillLossFn.apply(data, None, target, 1.0, 0.0, 0.0, 1.0)[0], data, target
+
+    def training_step(self, batch, batch_idx):
+        loss, data, target = self._loss_and_logits(batch, "train")
+        self.train_aprc(data.detach(), target.int())
+        self.log("train/loss", loss, on_step=False, on_epoch=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        loss, data, target = self._loss_and_logits(batch, "val")
+        self.running_logits.append(torch.sigmoid(data))                  # :331-333
+        self.running_labels.append(target.int())
+        self.val_aprc(data, target.int())
+        self.log("val/loss", loss, on_epoch=True)
+        return loss
+
+    def test_step(self, batch, batch_idx):
+        _, data, target = self._loss_and_logits(batch, "test")
+        self.running_logits.append(torch.sigmoid(data))                  # :364-366
+        self.running_labels.append(target.int())
+
+    def translate_labels(self, label_vec):
+        names = ['Action', 'Adventure', 'Comedy', 'Crime', 'Documentary', 'Drama', 'Family', 'Fantasy', 'History', 'Horror',
+                 'Music', 'Mystery', 'Science Fiction', 'Thriller', 'War']
+        return [names[i] for i, l in enumerate(label_vec) if l]

@@ -66,9 +66,8 @@ class FusionTransformer(LightningModule):
     def __init__(self, in_dims, d=512, nhead=8, nhid=2048, nlayers=4, dropout=0.0, batch_size=8, frames=16,
                  n_classes=15, fusion="sum", pyramid=False, max_group=4, precision="bf16"):
         super().__init__()
-        self.save_hyperparameters(in_dims=tuple(in_dims), d=d, nhead=nhead, nhid=nhid, nlayers=nlayers, dropout=dropout,
-                                  batch_size=batch_size, frames=frames, n_classes=n_classes, fusion=fusion,
-                                  pyramid=pyramid, max_group=max_group, precision=precision)
+        in_dims = tuple(in_dims)
+        self.save_hyperparameters()
         self.mode = ops.Mode(precision)
         self.streams = nn.ModuleList([ExpertStream(D, d, nhead, nhid, nlayers, dropout, batch_size, frames) for D in in_dims])
         self.fusion = fusion

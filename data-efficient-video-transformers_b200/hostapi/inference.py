@@ -81,21 +81,77 @@ class GraphedForward:
     ``eval()`` first - a captured graph would replay the same dropout seeds).  ``fn`` may return a tensor or a tuple /
     list of tensors; the returned tensors are static buffers overwritten by the next call."""
 
-    def __init__(self, fn, example_inputs, warmup=2):
+    def __init__(self, fn, example_inputs, warmup=2, module=None):
+        """``module`` (default: ``fn.__self__`` when ``fn`` is a bound method of an nn.Module): the module whose weights the
+        graph reads.  The captured kernels hold the RAW ADDRESSES of the bf16 weight planes cached in ``ops.Mode`` at capture
+        time; a weight update that re-splits a parameter into new planes (a plain torch optimizer step, ``load_state_dict``:
+        anything that bumps ``Parameter._version`` outside ``optim.FlatOptimizer``, which refreshes its planes in place) would
+        leave the graph replaying stale or freed memory.  ``__call__`` therefore compares every parameter's version and
+        storage address with the ones recorded at capture and RE-CAPTURES the graph when any of them has changed."""
         self.fn = fn
+        self.module = module if module is not None else getattr(fn, "__self__", None)
+        if not isinstance(self.module, torch.nn.Module):
+            self.module = None
+        self.warmup = warmup
+        self.captures = 0
         self.static_in = [x.clone() for x in example_inputs]
+        self._capture()
+
+    def _weights_key(self):
+        if self.module is None:
+            return None
+        return tuple((id(p), p._version, p.data_ptr()) for p in self.module.parameters())
+
+    def _capture(self):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(warmup):          # lazy initialisation (kernel attributes, weight plane caches) stays out of the graph
-                fn(*self.static_in)
+            for _ in range(self.warmup):     # lazy initialisation (kernel attributes, weight plane caches) stays out of the graph
+                self.fn(*self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.static_out = fn(*self.static_in)
+            self.static_out = self.fn(*self.static_in)
+        self._planes = self._plane_key()
+        self._key = self._weights_key()
+        self.captures += 1
+
+    def _plane_key(self):
+        """Addresses of the bf16 operand planes the captured kernels read (every ``ops.Mode`` found on the module tree)."""
+        if self.module is None:
+            return None
+        modes = {id(m.mode): m.mode for m in self.module.modules() if isinstance(getattr(m, "mode", None), ops.Mode)}
+        key = []
+        for mode in modes.values():
+            for pid, ent in mode._wcache.items():
+                key.append((pid, ent[2].data_ptr(), ent[3].data_ptr() if ent[3] is not None else 0))
+        return tuple(sorted(key))
+
+    def _stale(self):
+        if self.module is None or self._key == self._weights_key():
+            return False
+        # the weights changed.  FlatOptimizer rewrites the cached planes in place and re-registers them under the new version:
+        # the addresses the graph holds are still the live ones, so only a change of a plane ADDRESS (or an entry that no
+        # longer matches its parameter's version, i.e. one the next eager call would re-split) invalidates the capture.
+        now = self._weights_key()
+        if len(now) != len(self._key) or any(a[0] != b[0] or a[2] != b[2] for a, b in zip(now, self._key)):
+            return True                      # a parameter moved (biases, LayerNorm and head weights are read in place)
+        modes = {id(m.mode): m.mode for m in self.module.modules() if isinstance(getattr(m, "mode", None), ops.Mode)}
+        params = {id(p): p for p in self.module.parameters()}
+        for mode in modes.values():
+            for pid, ent in mode._wcache.items():
+                p = params.get(pid)
+                if p is not None and (ent[0]() is not p or ent[1] != p._version):
+                    return True
+        if self._planes != self._plane_key():
+            return True
+        self._key = self._weights_key()
+        return False
 
     def __call__(self, *inputs):
+        if self._stale():
+            self._capture()
         if len(inputs) != len(self.static_in):
             raise ValueError(f"GraphedForward: expected {len(self.static_in)} inputs, got {len(inputs)}")
         for dst, src in zip(self.static_in, inputs):

@@ -49,7 +49,7 @@ class PositionalEncoding(LightningModule):
 class SimpleTransformer(LightningModule):
     def __init__(self, **kwargs):
         super().__init__()
-        self.save_hyperparameters(**kwargs)
+        self.save_hyperparameters()
         hp = self.hparams
         hp.setdefault("dropout", 0.5)
         hp.setdefault("n_classes", 15)

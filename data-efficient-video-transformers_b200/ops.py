@@ -345,6 +345,16 @@ def spatial_pool(x, out, col_offset):
     capi.call("tvt_spatial_pool_fwd", a, _stream())
 
 
+def spatial_pool_bwd(dpooled, dx, col_offset):
+    """dx [frames, C, H, W] = dpooled[:, col_offset:col_offset+C] / (H*W) broadcast over the map; dpooled fp32."""
+    _cuda(dpooled, dx)
+    if dpooled.dtype != torch.float32:
+        raise TvtError("spatial_pool_bwd: dpooled must be fp32")
+    frames, Cc = dx.shape[0], dx.shape[1]
+    a = capi.SpatialPoolBwdArgs(_p(dpooled), _p(dx), frames, Cc, dx.shape[2] * dx.shape[3], _rowmajor(dpooled), col_offset, _dt(dx), 0)
+    capi.call("tvt_spatial_pool_bwd", a, _stream())
+
+
 # ------------------------------------------------------------------------------------------ heads / loss
 def head_linear_fwd(x, w, b):
     _cuda(x, w, b)

@@ -250,6 +250,19 @@ typedef struct {
 } tvt_spatial_pool_args;
 TVT_API int tvt_spatial_pool_fwd(const tvt_spatial_pool_args* args, void* stream);
 
+/* Gradient of the spatial average pool (the feature maps come from a trainable CNN in the reference's TPN,
+ * src/models/TPN.py:46-53): dx[f, c, :] = dpooled[f, col_offset + c] / hw.  dpooled fp32 [frames, ld]; dx has
+ * the dtype of the forward input and must be 16-byte aligned. */
+typedef struct {
+  const void* dpooled;
+  void* dx;
+  int64_t frames, channels, hw;
+  int64_t ld, col_offset;
+  int32_t dtype;     /* of dx */
+  int32_t reserved;
+} tvt_spatial_pool_bwd_args;
+TVT_API int tvt_spatial_pool_bwd(const tvt_spatial_pool_bwd_args* args, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Classification / distillation loss, forward + gradient in one launch.
  * Replaces nn.BCEWithLogitsLoss (src/models/transformer.py:35,142; frame_transformer.py:89,251),

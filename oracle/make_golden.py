@@ -158,12 +158,69 @@ def case_collab(ref):
     return {"xs": xs, "out": o_ref.detach()}
 
 
+def case_vivit(ref):
+    """src/models/vit.py ViViT (small configuration) against the restatement; the reference's output is frozen."""
+    kw = dict(image_size=16, patch_size=8, num_classes=5, num_frames=3, dim=32, depth=1, heads=2, dim_head=16)
+    torch.manual_seed(SEED)
+    v_ref = ref.vit.ViViT(**kw).eval()
+    torch.manual_seed(SEED)
+    v_or = param.ViViT(**kw).eval()
+    assert list(v_ref.state_dict().keys()) == list(v_or.state_dict().keys())
+    assert all(torch.equal(a, b) for a, b in zip(v_ref.state_dict().values(), v_or.state_dict().values()))
+    g = torch.Generator().manual_seed(SEED)
+    x = torch.randn(2, 3, 3, 16, 16, generator=g)
+    o_ref, o_or = v_ref(x.clone()), v_or(x.clone())
+    assert torch.allclose(o_ref, o_or, atol=1e-6)
+    return {"kw": kw, "out": o_ref.detach(), "state_dict_keys": list(v_ref.state_dict().keys())}
+
+
+def case_frame_transformer(ref):
+    """The UNMODIFIED FrameTransformer(**config.yaml) in its one runnable mode ("vid"): real R(2+1)D-18 backbone
+    (torchvision's architecture, seeded random weights: no network), forward + training loss on a seeded batch, against
+    oracle.param.FrameTransformer with the same backbone module and weights.  Also freezes the reference's constructor
+    contract: config.yaml's keys, the hyper-parameters it stores and its state_dict key / shape list."""
+    import yaml
+    ft = ref_loader.load_frame_transformer()
+    cfg = yaml.safe_load(open(os.path.join(ref_loader.REF_ROOT, "src/config.yaml")))
+    torch.manual_seed(SEED)
+    m_ref = ft.FrameTransformer(**cfg)
+    g = torch.Generator().manual_seed(SEED)
+    B = cfg["batch_size"]
+    vid = torch.randn(B, 13, 12, 3, 112, 112, generator=g) * 0.5
+    target = (torch.rand(B, 19, generator=g) < 0.15).double()
+    for sub in m_ref.modules():
+        if isinstance(sub, nn.Dropout):
+            sub.p = 0.0                      # position_encoder / encoder dropout 0.5 is hard-coded (:92,99)
+        if isinstance(sub, nn.MultiheadAttention):
+            sub.dropout = 0.0                # attention-probability dropout is a float attribute, not a module
+    m_ref.train()
+    loss = m_ref.training_step((target, None, vid), 0)
+    loss.backward()
+    logits = m_ref(None, vid).detach()
+    m_or = param.FrameTransformer(model="vid", batch_size=B, seq_len=13, cls=1, dropout=0.0, vid_model=m_ref.vid_model)
+    sd = {k: v for k, v in m_ref.state_dict().items() if not k.startswith("vid_model.")}
+    missing = m_or.load_state_dict(sd, strict=False)
+    assert all(k.startswith("vid_model.") for k in missing.missing_keys) and not missing.unexpected_keys
+    m_or.train()
+    assert torch.allclose(m_or(None, vid), logits, atol=1e-5)
+    assert torch.allclose(m_or.loss((target, None, vid)), loss.detach().float(), atol=1e-6)
+    head_grad = m_ref.img_mlp_head[4].weight.grad.detach().double().norm().float()
+    return {"config": cfg, "hparams": {k: v for k, v in m_ref.hparams.items()},
+            "state_dict_shapes": {k: tuple(v.shape) for k, v in m_ref.state_dict().items()},
+            "logits": logits, "loss": loss.detach().float(), "head_grad_norm": head_grad,
+            "simple_transformer_state_dict_shapes": {k: tuple(v.shape) for k, v in
+                                                     ref.transformer.SimpleTransformer(**dict(cfg, model="ptn")).state_dict().items()},
+            "tpn_state_dict_keys": {name: list(getattr(ref.tpn, name)().state_dict().keys())
+                                    for name in ("Feature_Pyramid_low", "Feature_Pyramid_Mid", "Feature_Pyramid_High", "Reasoning")}}
+
+
 def main():
     if not ref_loader.available():
         sys.exit("reference not available: golden vectors can only be regenerated where /root/reference exists")
     ref = ref_loader.load()
     gold = {"seed": SEED, "torch": torch.__version__}
-    for fn in (case_ptn, case_posenc, case_reasoning, case_vit, case_spatial_pyramid, case_frame_stream, case_collab):
+    for fn in (case_ptn, case_posenc, case_reasoning, case_vit, case_spatial_pyramid, case_frame_stream, case_collab, case_vivit,
+               case_frame_transformer):
         gold[fn.__name__[5:]] = fn(ref)
         print("ok", fn.__name__)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

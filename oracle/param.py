@@ -414,3 +414,133 @@ class CollaborativeGating(nn.Module):
             work.append(c)
         B, S = total.shape[:2]
         return self.geu(total.reshape(B * S, -1)).reshape(B, S, -1)
+
+
+# ------------------------------------------------------------------ FrameTransformer (two-stream model)
+class FrameTransformer(nn.Module):
+    """src/models/frame_transformer.py:83-244 with the widths as arguments and the CNN backbones injected.
+
+    ``vid_model`` / ``img_model`` map the stacked raw clips / frames to one ``d``-wide feature vector each
+    (VidResNet / ImgResNet, :50-74); ``None`` = FEATURE MODE: the inputs already are backbone features
+    (``vid`` (B, S-1, d), ``img`` (B, S-1, d)) and the learned CLS inputs ``vid_cls`` / ``img_cls`` are (1, d) feature
+    rows instead of a raw (1, 12, 3, 112, 112) clip / (1, 3, 224, 224) frame.  Everything after the backbone follows the
+    reference statement by statement: per-clip CLS concat (:193-196, :213-216), ``view(batch_size, S, d)`` (:204, :222),
+    seq-first PE + TransformerBase (:205-208, :227-231), CLS = token 0 (:209, :233), GELU head (:106).
+
+    What the reference cannot run at this commit, and how it is read here (each restoration is the minimal one):
+      * ``img_model`` / ``scene_transformer`` / ``img_cls`` are commented out (:94,98,104) but used by every mode except
+        "vid": restored exactly as written in those comments (TransformerBase(d, d, 4, d, 4, 0.5)).
+      * "sum": ``torch.cat((data, distil_inject))`` (:226) joins a (S, B, d) sequence with a (B, d) CLS vector — read as
+        ``distil_inject.unsqueeze(0)``; the S + 1 tokens need ``max_len >= S + 1`` in the PositionalEncoding (:91-93).
+      * "distil": ``forward`` returns the image stream's (CLS, last token) d-wide vectors and ``training_step`` feeds
+        them to BCE against (B, n_classes) targets (:247-251) — a shape error; read as student = head(img CLS),
+        teacher = head(video CLS) (the quantities the loss names ``img`` / ``vid`` suggest).
+      * "pre_modal": ``vid = self.vid_step`` (:188, no call) and the mode string tested in ``img_step`` is "pre-modal"
+        (:219), so no injection ever happens: what executes is identical to "frame".
+      * "sum_residual" normalises ``img_cls`` twice and never uses ``vid_cls`` (:157-158): reproduced as written.
+    """
+
+    def __init__(self, model="vid", batch_size=2, seq_len=13, cls=1, d=896, n_classes=19, dropout=0.5, nlayers=4,
+                 vid_model=None, img_model=None, **_unused):
+        super().__init__()
+        self.model, self.batch_size, self.d = model, batch_size, d
+        self.seq_len = seq_len + (1 if cls else 0)                                   # :86-87
+        self.criterion = nn.BCEWithLogitsLoss()
+        self.distil_criterion = nn.CrossEntropyLoss()
+        self.position_encoder = PositionalEncoding(d, dropout, max_len=self.seq_len + (1 if model == "sum" else 0))
+        self.vid_model = vid_model
+        self.distil_transformer = TransformerBase(d, 128, 2, 512, nlayers, dropout)  # :99
+        self.vid_cls = nn.Parameter(torch.rand(1, d) if vid_model is None else torch.rand(1, 12, 3, 112, 112))
+        self.img_mlp_head = nn.Sequential(nn.Linear(d, 512), nn.GELU(), nn.Linear(512, 128), nn.GELU(), nn.Linear(128, n_classes))
+        self.norm = nn.LayerNorm(d)                                                  # :115 (unused)
+        if model != "vid":
+            self.img_model = img_model                                               # :94
+            self.scene_transformer = TransformerBase(d, d, 4, d, nlayers, dropout)  # :98
+            self.img_cls = nn.Parameter(torch.rand(1, d) if img_model is None else torch.rand(1, 3, 224, 224))  # :104
+
+    def _stack(self, cls, data, backbone):
+        total = [torch.cat((cls, data[i]), dim=0) for i in range(len(data))]         # :193-196
+        x = torch.stack(total)
+        if backbone is not None:
+            x = backbone(x.view(-1, *x.shape[2:]))
+        return x.reshape(self.batch_size, self.seq_len, self.d)
+
+    def vid_step(self, data):
+        x = self._stack(self.vid_cls, data, None if self.vid_model is None else
+                        (lambda t: self.vid_model(t.permute(0, 2, 1, 3, 4))))       # :198-204
+        x = self.distil_transformer(self.position_encoder(x.permute(1, 0, 2))).permute(1, 0, 2)
+        return x[:, 0]
+
+    def img_step(self, data, distil_inject):
+        x = self._stack(self.img_cls, data, self.img_model).permute(1, 0, 2)          # :213-223
+        if self.model == "sum":
+            x = torch.cat((x, distil_inject.unsqueeze(0)))                            # :225-226
+        seq = self.scene_transformer(self.position_encoder(x)).permute(1, 0, 2)
+        cls = seq[:, 0]
+        if self.model in ("distil", "sum"):
+            return cls, seq[:, -1]                                                    # :234-239
+        if self.model == "sum_residual":
+            return cls, seq
+        return self.img_mlp_head(cls)
+
+    def forward(self, img, vid):
+        m = self.model
+        if m == "distil":
+            vid_cls = self.vid_step(vid)
+            img_cls, _ = self.img_step(img, vid_cls)
+            return self.img_mlp_head(img_cls), self.img_mlp_head(vid_cls)
+        if m == "sum":
+            img_cls, vid_tkn = self.img_step(img, self.vid_step(vid))
+            return self.img_mlp_head(img_cls + vid_tkn)                               # :143-147
+        if m == "sum_residual":
+            self.vid_step(vid)
+            img_cls, _ = self.img_step(img, None)
+            a = F.normalize(img_cls, p=2.0, dim=-1)
+            b = F.normalize(a, p=2.0, dim=-1)                                         # :157-158 (img_cls again)
+            return self.img_mlp_head(a + b)
+        if m in ("frame", "pre_modal"):
+            return self.img_step(img, None)                                           # :172-178
+        if m == "vid":
+            return self.img_mlp_head(self.vid_step(vid))                              # :179-182
+        return None
+
+    def loss(self, batch):
+        """training_step, frame_transformer.py:246-282."""
+        target, img, vid = batch
+        if self.model == "distil":
+            s, t = self(img, vid)
+            return self.criterion(s, target.float()) + self.distil_criterion(s, torch.argmax(t, dim=-1))
+        return self.criterion(self(img, vid), target.float())
+
+
+class ViViT(nn.Module):
+    """src/models/vit.py:79-128: patch embedding (einops Rearrange + Linear), per-frame space transformer over
+    (space token + patches) with a learned (1, frames, patches + 1, dim) positional embedding, then a temporal transformer
+    over (temporal token + per-frame CLS vectors), cls / mean pooling, LayerNorm + Linear head."""
+
+    def __init__(self, image_size, patch_size, num_classes, num_frames, dim=192, depth=4, heads=3, pool="cls", in_channels=3,
+                 dim_head=64, dropout=0.0, emb_dropout=0.0, scale_dim=4):
+        super().__init__()
+        from einops.layers.torch import Rearrange
+        num_patches = (image_size // patch_size) ** 2
+        patch_dim = in_channels * patch_size ** 2
+        self.to_patch_embedding = nn.Sequential(
+            Rearrange("b t c (h p1) (w p2) -> b t (h w) (p1 p2 c)", p1=patch_size, p2=patch_size), nn.Linear(patch_dim, dim))
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_frames, num_patches + 1, dim))
+        self.space_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.space_transformer = VitTransformer(dim, depth, heads, dim_head, dim * scale_dim, dropout)
+        self.temporal_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.temporal_transformer = VitTransformer(dim, depth, heads, dim_head, dim * scale_dim, dropout)
+        self.dropout = nn.Dropout(emb_dropout)
+        self.pool = pool
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
+
+    def forward(self, x):
+        x = self.to_patch_embedding(x)
+        b, t, n, d = x.shape
+        x = torch.cat((self.space_token.expand(b, t, 1, d), x), dim=2)
+        x = self.dropout(x + self.pos_embedding[:, :, :(n + 1)])
+        x = self.space_transformer(x.reshape(b * t, n + 1, d))[:, 0].reshape(b, t, d)
+        x = self.temporal_transformer(torch.cat((self.temporal_token.expand(b, 1, d), x), dim=1))
+        x = x.mean(dim=1) if self.pool == "mean" else x[:, 0]
+        return self.mlp_head(x)

@@ -1,5 +1,33 @@
-"""Helpers shared by the parity tests."""
+"""Helpers shared by the parity tests.
+
+Every comparison made through ``assert_close`` / ``grads_close`` with a ``case=`` name is also RECORDED (error,
+tolerance, the stock-PyTorch-bf16 yardstick error and whether the yardstick clause was needed), so that the
+softening of the bf16 gradient bar is auditable: ``conftest.pytest_terminal_summary`` prints one line per case
+(``N params, worst e, K exemptions, worst exempt ratio``) — which therefore lands in the driver's GPUTEST tail —
+and writes the full per-parameter table to ``profiles/parity_report.json`` (and ``gpurun_out/`` on a GPU box).
+"""
 import torch
+
+# recorded comparisons: list of dicts (see _record)
+REPORT = []
+# free-form one-line notes for the terminal summary (top-1 agreement counts, margin histograms ...)
+NOTES = []
+# set by conftest's autouse fixture for gpu-marked tests: the default `case` of assert_close / grads_close
+CURRENT_CASE = [None]
+
+# The only parameters that may use the yardstick clause (bf16 mode): ReLU-gated FFN-in gradients (gate flips of
+# near-zero pre-activations) and per-batch-slot CLS rows (single-token gradients, no averaging over tokens).
+# Anything else exceeding the tolerance fails outright, whatever stock PyTorch bf16 does.
+EXEMPTIBLE = ("linear1.", "cls")
+
+
+def _record(case, what, err, tol, yard=None, exempt=False, limit=None):
+    case = case if case is not None else CURRENT_CASE[0]
+    if case is None:
+        return
+    REPORT.append({"case": case, "what": what, "err": float(err), "tol": float(tol),
+                   "yardstick_err": None if yard is None else float(yard), "exempt": bool(exempt),
+                   "limit": float(tol if limit is None else limit)})
 
 
 def rel_err(a, b):
@@ -9,8 +37,9 @@ def rel_err(a, b):
     return (a - b).norm().item() / (den if den > 0 else 1.0)
 
 
-def assert_close(a, b, tol, what=""):
+def assert_close(a, b, tol, what="", case=None):
     e = rel_err(a.cpu(), b.cpu())
+    _record(case, what, e, tol)
     assert e <= tol, f"{what}: relative error {e:.3e} > {tol:.1e}"
     return e
 
@@ -22,16 +51,18 @@ def copy_state(dst, src):
     return dst
 
 
-def grads_close(mod, ref, tol, what="", skip=(), yard=None, slack=1.5):
+def grads_close(mod, ref, tol, what="", skip=(), yard=None, slack=1.5, case=None, exemptible=EXEMPTIBLE):
     """Every parameter gradient of `mod` matches `ref`'s within normwise tolerance `tol`.
 
     `yard` (optional) is a copy of the fp32 oracle whose gradients were computed under stock
-    torch.autocast(bf16): a parameter may exceed `tol` only if stock PyTorch bf16 does so too, and then by at
-    most `slack` x the yardstick's own error (ReLU-gate flips and single-token CLS rows are inherently noisy
-    in bf16 for any implementation).  Returns (worst name, worst error, number of yardstick exemptions)."""
+    torch.autocast(bf16): a parameter whose name contains one of `exemptible` may exceed `tol` only if stock
+    PyTorch bf16 does so too, and then by at most `slack` x the yardstick's own error (ReLU-gate flips and
+    single-token CLS rows are inherently noisy in bf16 for any implementation).  Every comparison is recorded
+    under `case` for the parity report.  Returns (worst name, worst error, number of yardstick exemptions)."""
     rp = dict(ref.named_parameters())
     yp = dict(yard.named_parameters()) if yard is not None else {}
     worst, exempt = ("", 0.0), 0
+    failures = []
     for name, p in mod.named_parameters():
         if any(s in name for s in skip):
             continue
@@ -46,9 +77,41 @@ def grads_close(mod, ref, tol, what="", skip=(), yard=None, slack=1.5):
         e = rel_err(p.grad.cpu(), g_ref.cpu())
         if e > worst[1]:
             worst = (name, e)
-        limit = tol
-        if e > tol and name in yp and yp[name].grad is not None:
-            limit = max(tol, slack * rel_err(yp[name].grad.cpu(), g_ref.cpu()))
+        limit, ye, used = tol, None, False
+        if name in yp and yp[name].grad is not None:
+            ye = rel_err(yp[name].grad.cpu(), g_ref.cpu())
+        if e > tol and ye is not None and any(s in name for s in exemptible):
+            limit = max(tol, slack * ye)
+            used = True
             exempt += 1
-        assert e <= limit, f"{what}{name}: gradient relative error {e:.3e} > {limit:.1e}"
+        _record(case, "grad " + name, e, tol, ye, used, limit)
+        if e > limit:
+            failures.append(f"{what}{name}: gradient relative error {e:.3e} > {limit:.1e}"
+                            + (f" (stock bf16 yardstick {ye:.3e})" if ye is not None else ""))
+    assert not failures, "; ".join(failures)
     return worst[0], worst[1], exempt
+
+
+def summarize():
+    """Per-case one-liners + the full table (for conftest.pytest_terminal_summary)."""
+    cases = {}
+    for r in REPORT:
+        cases.setdefault(r["case"], []).append(r)
+    lines = []
+    for case, rows in cases.items():
+        grads = [r for r in rows if r["what"].startswith("grad ")]
+        other = [r for r in rows if not r["what"].startswith("grad ")]
+        ex = [r for r in grads if r["exempt"]]
+        parts = [f"parity[{case}]:"]
+        if other:
+            parts.append(", ".join(f"{r['what']} {r['err']:.2e}" for r in other))
+        if grads:
+            w = max(grads, key=lambda r: r["err"])
+            parts.append(f"{len(grads)} param grads, worst {w['err']:.2e} ({w['what'][5:]}), tol {w['tol']:.0e}, "
+                         f"{len(ex)} yardstick exemptions")
+            if ex:
+                wr = max(ex, key=lambda r: r["err"] / max(r["yardstick_err"], 1e-30))
+                parts.append(f"worst exempt ratio {wr['err'] / max(wr['yardstick_err'], 1e-30):.2f}x stock-bf16 "
+                             f"({wr['what'][5:]}: {wr['err']:.2e} vs {wr['yardstick_err']:.2e})")
+        lines.append(" ".join(parts))
+    return lines
