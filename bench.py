@@ -43,6 +43,8 @@ WORKLOADS = {
                teacher=(2048, 1024, 128), student_dims=(2048,), pyramid=True, distill=True),
 }
 N_CLASSES = 15
+# whole-step CUDA-graph replay for the launch-bound configs (C1-C4) unless --graph says otherwise
+GRAPH_SMALL_CONFIGS = False
 
 
 def flops_per_clip(w):
@@ -222,77 +224,89 @@ def gpu_step(w, model, reducer, opt, xs, y):
     return loss
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="tvt", choices=["tvt", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--dropout", type=float, default=0.5, help="config.yaml dropout (0.5 in the reference)")
-    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's)")
-    ap.add_argument("--cpu-clips", type=int, default=0, help="clips per step of the CPU baseline sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--breakdown", default="", help="write the per-kernel CUDA-event breakdown to this file")
-    args = ap.parse_args()
-    w = dict(WORKLOADS[args.workload])
-    if args.batch:
-        w["batch"] = args.batch
-    args.warmup = max(args.warmup, 3) if args.impl == "tvt" else args.warmup
+def time_torch_gpu(w, B, dev, steps=5, warmup=3):
+    """The library path on the SAME GPU: the oracle's torch.nn composition (what the reference's modules dispatch to)
+    under stock bf16 autocast — cuBLAS GEMMs, ATen SDPA, ATen LayerNorm, fused AdamW.  SURVEY fact 1: this, not the CPU,
+    is the kernel path to beat.  Returns clips/s, ms/step."""
+    from oracle import param
+    teacher, student = build_oracle(w, B)
+    student.to(dev)
+    if teacher is not None:
+        teacher.to(dev)
+    opt = torch.optim.AdamW(student.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
+    xs, y = synth_batch(w, B, 1130, device=dev)
+    ns = len(w["student_dims"])
 
-    rank = int(os.environ.get("RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, w, rank)
-        return
+    def step():
+        opt.zero_grad(set_to_none=False)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if teacher is not None:
+                with torch.no_grad():
+                    t_logits, _ = teacher(xs)
+                s_logits, pyr = student(xs[:ns])
+            else:
+                s_logits, pyr = student(xs)
+                t_logits = None
+        pyr = None if pyr is None else pyr.float().clamp(1e-6, 1 - 1e-6)
+        if t_logits is not None:
+            loss, _ = param.distill_loss(s_logits.float(), t_logits.float(), y, temperature=2.0, alpha=1.0, pyramid=pyr)
+        else:
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(s_logits.float(), y)
+            if pyr is not None:
+                loss = loss + torch.nn.functional.binary_cross_entropy(pyr, y)
+        loss.backward()
+        opt.step()
 
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del teacher, student, opt, xs, y
+    torch.cuda.empty_cache()
+    return B / ms * 1e3, ms
+
+
+def run_tvt(w, args, ctx, steps, warmup, sample_clocks=False, graph=None):
+    """One workload on this rank's GPU: W warm-up + K timed steps with resident inputs, K timed steps end to end from
+    pinned host batches, one CUDA-event-instrumented step.  Returns a dict of raw measurements (max over ranks)."""
     import torch.distributed as dist
-    import tvt_b200
-    from tvt_b200 import capi, ddp
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the tvt arm has no CPU path (use --impl reference for the CPU oracle)")
-    # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG=VERSION/WARN ignore
-    # NCCL_DEBUG_FILE): create it now, with file descriptor 1 pointed at stderr, so stdout carries the JSON line only
-    sys.stdout.flush()
-    saved_fd = os.dup(1)
-    os.dup2(2, 1)
-    try:
-        rank, local, world = ddp.init_from_env()
-        dev = torch.device("cuda", local)
-        if world > 1:
-            dist.all_reduce(torch.zeros(1, device=dev))
-            torch.cuda.synchronize()
-    finally:
-        sys.stdout.flush()
-        os.dup2(saved_fd, 1)
-        os.close(saved_fd)
-    capi.load()
-    if capi.load().tvt_device_check() != 0:
-        raise SystemExit("bench.py: " + capi.last_error())
+    from tvt_b200 import capi, ddp, optim
+    rank, local, world, dev = ctx
     B = w["batch"]
+    graph = args.graph if graph is None else graph
     model = build_model(w, B, args.precision, args.dropout, dev)
     trainable = [p for p in model.parameters() if p.requires_grad]
     reducer = ddp.GradBucketReducer(trainable, bucket_bytes=32 << 20, average=False)
     student = model.student if w["teacher"] else model
-    from tvt_b200 import optim
     # flat-bucket AdamW: one launch per gradient bucket, 1 / world averaging and bf16 weight planes fused
     opt = optim.FlatOptimizer(reducer, modes=[student.mode], kind="adamw", lr=1e-4, weight_decay=0.01)
 
-    # two resident batches (alternated) + the same two as pinned host batches for the e2e leg
-    host = [synth_batch(w, B, 1130 + rank + 1000 * i, pin=True) for i in range(2)]
+    # two resident batches (alternated) + the same two as pinned host batches for the e2e leg.  Host features are stored
+    # in the compute dtype (bf16 mode: bf16 — what a feature store for this path holds; the model's first op is that cast)
+    hdt = torch.bfloat16 if (args.precision == "bf16" and args.host_dtype == "bf16") else torch.float32
+    host = []
+    for i in range(2):
+        xs, y = synth_batch(w, B, 1130 + rank + 1000 * i)
+        host.append(([x.to(hdt).pin_memory() for x in xs], y.pin_memory()))
     resident = [([x.to(dev) for x in xs], y.to(dev)) for xs, y in host]
-    h2d_bytes = sum(x.numel() * 4 for x in host[0][0]) + host[0][1].numel() * 4
+    h2d_bytes = sum(x.numel() * x.element_size() for x in host[0][0]) + host[0][1].numel() * 4
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(run_one, steps, finish=None):
+    def timed(run_one, nsteps, finish=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for i in range(steps):
+        for i in range(nsteps):
             run_one(i)
         if finish is not None:
             finish()
@@ -303,18 +317,28 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
-        return ms / steps
+        return ms / nsteps
+
+    stepper = None
+    if graph:
+        from tvt_b200.hostapi import GraphedTrainStep
+        stepper = GraphedTrainStep(lambda xs, y: gpu_step(w, model, reducer, opt, xs, y), resident[0], warmup=3)
+        step_fn = lambda xs, y: stepper(xs, y)            # noqa: E731
+    else:
+        step_fn = lambda xs, y: gpu_step(w, model, reducer, opt, xs, y)   # noqa: E731
 
     # ---- leg 1: inputs resident in HBM
-    for i in range(args.warmup):
-        gpu_step(w, model, reducer, opt, *resident[i % 2])
-    sampler = ClockSampler(local)
-    if rank == 0:
+    for i in range(warmup):
+        step_fn(*resident[i % 2])
+    sampler = ClockSampler(local) if sample_clocks else None
+    if sampler is not None and rank == 0:
         sampler.start()
     l0 = capi.launches
-    ms = timed(lambda i: gpu_step(w, model, reducer, opt, *resident[i % 2]), args.steps)
-    launches = (capi.launches - l0) // args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    ms = timed(lambda i: step_fn(*resident[i % 2]), steps)
+    launches = (capi.launches - l0) // steps
+    if stepper is not None:
+        launches = stepper.kernels_per_replay
+    clocks = sampler.stop() if (sampler is not None and rank == 0) else None
 
     # ---- leg 2: end to end from pinned host batches, copies prefetched on a side stream
     copy_stream = torch.cuda.Stream(device=dev)
@@ -356,7 +380,7 @@ def main():
         torch.cuda.current_stream().wait_event(state["ev"])
         xs, y = slots[i % 2]
         state["ev"] = prefetch(i + 1)                       # next step's inputs copy while this step computes
-        loss = gpu_step(w, model, reducer, opt, xs, y)
+        loss = step_fn(xs, y)
         buf = loss_host[i % 2]
         buf.copy_(loss.detach().reshape(1).float(), non_blocking=True)
         ev = torch.cuda.Event()
@@ -368,58 +392,52 @@ def main():
     e2e_one(0)
     read_pending()
     state["ev"] = None
-    ms_e2e = timed(e2e_one, args.steps, finish=read_pending)
-    assert len(losses) == args.steps + 1 and all(math.isfinite(v) for v in losses), "e2e leg: a step's loss was not read back"
+    ms_e2e = timed(e2e_one, steps, finish=read_pending)
+    assert len(losses) == steps + 1 and all(math.isfinite(v) for v in losses), "e2e leg: a step's loss was not read back"
+
+    # ---- data-parallel replicas must hold identical parameters after the same number of identical updates
+    checksum_equal = None
+    if world > 1:
+        cs = torch.zeros(2, dtype=torch.float64, device=dev)
+        for b in opt.buckets:
+            cs[0] += b["p"].double().sum()
+            cs[1] += b["p"].double().abs().sum()
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        checksum_equal = bool(torch.equal(lo, hi))
+        assert checksum_equal, f"rank {rank}: parameter checksums differ across ranks after training: {lo.tolist()} vs {hi.tolist()}"
 
     # ---- instrumented step: CUDA events around every kernel-launching C-ABI call (not part of the timings)
     breakdown = capi.profile_step(lambda: gpu_step(w, model, reducer, opt, *resident[0]))
-    gemm = breakdown.get("tvt_gemm", {"ms": 0.0, "flops": 0.0, "calls": 0})
+    detail = dict(capi.last_profile_detail)
+    out = {"ms": ms, "ms_e2e": ms_e2e, "launches": int(launches), "h2d_bytes": h2d_bytes, "clocks": clocks, "breakdown": breakdown,
+           "detail": detail, "checksum_equal": checksum_equal, "host_dtype": str(hdt).replace("torch.", ""), "graph": bool(graph),
+           "final_loss": losses[-1]}
+    reducer.remove()
+    del model, reducer, opt, stepper, step_fn, resident, slots, host, student, trainable
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
 
-    peaks = {}
+def load_peaks():
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
-        pass
+        return {}
+
+
+def summarize_kernels(w, r, peaks):
+    """Dominant kernel (GEMM) roofline + the attention metric from the instrumented step of run ``r``."""
+    B = w["batch"]
+    breakdown = r["breakdown"]
+    gemm = breakdown.get("tvt_gemm", {"ms": 0.0, "flops": 0.0, "calls": 0})
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
-    traffic = None
-    try:   # dram__bytes_read + write per launch from the committed ncu --set full capture of this kernel
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))["mean_dram_bytes_per_launch"]
-    except Exception:
-        pass
     total_ms = sum(v["ms"] for v in breakdown.values()) or 1.0
-    fl = flops_per_clip(w)
-    value = world * B / (ms * 1e-3)
-    line = {
-        "metric": "train clips/sec fwd+bwd", "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": w["desc"], "clips_per_gpu": B, "global_batch": world * B, "frames": w["frames"], "d_model": w["d"],
-                   "layers": w["layers"], "heads": w["heads"], "ff": w["ff"], "dropout": args.dropout, "optimizer": "AdamW (tvt flat-bucket kernel)",
-                   "parallelism": f"dp{world}", "l2": "inputs larger than L2 (%.0f MB per step, two alternating batches)" % (h2d_bytes / 1e6),
-                   "gflop_per_clip_step": round(fl / 1e9, 2)},
-        "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e, 3),
-                "loss_read": "every step, via pinned memory, collected one step later (after the next step is enqueued); the last inside the timed region"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "model_tflops": round(value / world * fl / 1e12, 1),
-        "model_frac_of_peak": round(value / world * fl / 1e12 / peak_tf, 4),
-        "roofline": {"kernel": "tvt::gemm::gemm_kernel (tcgen05)", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": traffic, "peak_source": peak_src,
-                     "launches_per_step": gemm["calls"], "share_of_kernel_time": round(gemm["ms"] / total_ms, 4)},
-    }
-    # BASELINE.json's second metric: attention TFLOP/s against the bf16 peak (un-padded algorithmic FLOPs of every attention
-    # launch of the instrumented step).  At S = frames + 1 <= 129 and head_dim 64 the kernels have S / 2 FLOP per HBM byte, below
-    # the ridge, so the bandwidth figure (q, k, v, o / their gradients, bf16) is the roofline that actually bounds them.
-    n_tok, burst = B * (w["frames"] + 1), peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained", 1400.0))
+    n_tok, burst = B * (w["frames"] + 1), peaks.get("bf16_tflops", peak_tf)
     att = {}
     for name, tensors in (("fwd", 4), ("bwd", 8)):
         v = breakdown.get(f"tvt_attention_{name}")
@@ -429,20 +447,179 @@ def main():
             att[name] = {"tflops": round(tf, 1), "frac_of_bf16_peak": round(tf / burst, 4), "hbm_gbs": round(gbs, 1),
                          "frac_of_hbm_peak": round(gbs / peaks.get("hbm_gbs", 6500.0), 4), "launches_per_step": v["calls"],
                          "us_per_launch": round(v["ms"] * 1e3 / v["calls"], 1)}
+    shares = {k: round(v["ms"] / total_ms, 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])[:6]}
+    return gemm, achieved, peak_tf, total_ms, att, shares
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="tvt", choices=["tvt", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dropout", type=float, default=0.5, help="config.yaml dropout (0.5 in the reference)")
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: the workload's batch is the GLOBAL batch, split evenly over the ranks (SURVEY 8e: C4 256 -> 128/64/32)")
+    ap.add_argument("--host-dtype", default="bf16", choices=["bf16", "fp32"], help="dtype of the pinned host feature batches (e2e leg)")
+    ap.add_argument("--graph", type=int, default=-1, help="1: replay the whole training step as a CUDA graph; 0: eager launches; "
+                                                          "-1 (default): graph for the launch-bound configs c1-c4, eager for c5")
+    ap.add_argument("--cpu-clips", type=int, default=0, help="clips per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1-C4 lines and the stock-PyTorch-on-GPU yardstick")
+    ap.add_argument("--breakdown", default="", help="write the per-kernel CUDA-event breakdown to this file")
+    args = ap.parse_args()
+    args.graph_explicit = args.graph >= 0
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["batch"] = args.batch
+    args.warmup = max(args.warmup, 3) if args.impl == "tvt" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    import torch.distributed as dist
+    import tvt_b200  # noqa: F401
+    from tvt_b200 import capi, ddp
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the tvt arm has no CPU path (use --impl reference for the CPU oracle)")
+    # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG=VERSION/WARN ignore
+    # NCCL_DEBUG_FILE): create it now, with file descriptor 1 pointed at stderr, so stdout carries the JSON line only
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local, world = ddp.init_from_env()
+        dev = torch.device("cuda", local)
+        if world > 1:
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
+    capi.load()
+    if capi.load().tvt_device_check() != 0:
+        raise SystemExit("bench.py: " + capi.last_error())
+    ctx = (rank, local, world, dev)
+    global_batch = w["batch"] * world
+    if args.scaling == "strong":
+        if w["batch"] % world:
+            raise SystemExit(f"bench.py: --scaling strong needs the global batch {w['batch']} divisible by {world} ranks")
+        global_batch = w["batch"]
+        w["batch"] //= world
+    B = w["batch"]
+    use_graph = (GRAPH_SMALL_CONFIGS and args.workload != "c5") if args.graph < 0 else bool(args.graph)
+    args.graph = use_graph
+    r = run_tvt(w, args, ctx, args.steps, args.warmup, sample_clocks=True)
+
+    # ---- the other BASELINE configs (C1-C4), few steps each, same legs; C4 also with its strong-scaling split
+    extras = {}
+    if not args.no_extras and args.workload == "c5":
+        for name in ("c1", "c2", "c3", "c4"):
+            for scaling in (("weak", "strong") if (name == "c4" and world > 1) else ("weak",)):
+                wx = dict(WORKLOADS[name])
+                gb = wx["batch"] * world
+                if scaling == "strong":
+                    gb = wx["batch"]
+                    wx["batch"] //= world
+                rx = run_tvt(wx, args, ctx, min(args.steps, 20), 3, graph=(args.graph if args.graph_explicit else GRAPH_SMALL_CONFIGS))
+                extras[name if scaling == "weak" else name + "_strong"] = (wx, gb, scaling, rx)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    gemm, achieved, peak_tf, total_ms, att, shares = summarize_kernels(w, r, peaks)
+    traffic = None
+    try:   # dram__bytes_read + write per launch from the committed ncu --set full capture of this kernel
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))["mean_dram_bytes_per_launch"]
+    except Exception:
+        pass
+    fl = flops_per_clip(w)
+    ms, ms_e2e = r["ms"], r["ms_e2e"]
+    value = world * B / (ms * 1e-3)
+    line = {
+        "metric": "train clips/sec fwd+bwd", "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": w["desc"], "clips_per_gpu": B, "global_batch": global_batch, "frames": w["frames"], "d_model": w["d"],
+                   "layers": w["layers"], "heads": w["heads"], "ff": w["ff"], "dropout": args.dropout, "optimizer": "AdamW (tvt flat-bucket kernel)",
+                   "parallelism": f"dp{world}", "l2": "inputs larger than L2 (%.0f MB per step, two alternating batches)" % (r["h2d_bytes"] / 1e6),
+                   "gflop_per_clip_step": round(fl / 1e9, 2), "host_feature_dtype": r["host_dtype"],
+                   "launch_mode": "whole-step CUDA graph replay" if r["graph"] else "eager launches chained with programmatic dependent launch"},
+        "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 1), "unit": "clips/s", "h2d_bytes_per_step": r["h2d_bytes"], "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e, 3),
+                "loss_read": "every step, via pinned memory, collected one step later (after the next step is enqueued); the last inside the timed region"},
+        "gpu_launches": int(r["launches"]),
+        "clocks": r["clocks"],
+        "model_tflops": round(value / world * fl / 1e12, 1),
+        "model_frac_of_peak": round(value / world * fl / 1e12 / peak_tf, 4),
+        "roofline": {"kernel": "tvt::gemm::gemm_kernel (tcgen05)", "bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": traffic,
+                     "traffic_source": "constant: mean dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full "
+                                       "capture (profiles/gemm_traffic.json), not measured in this run",
+                     "peak_source": peak_src, "launches_per_step": gemm["calls"], "share_of_kernel_time": round(gemm["ms"] / total_ms, 4)},
+        "kernel_time_shares": shares,
+    }
+    if r["checksum_equal"] is not None:
+        line["ranks_hold_identical_parameters"] = r["checksum_equal"]
+    # BASELINE.json's second metric: attention TFLOP/s against the bf16 peak (un-padded algorithmic FLOPs of every attention
+    # launch of the instrumented step).  At S = frames + 1 <= 129 and head_dim 64 the kernels have S / 2 FLOP per HBM byte, below
+    # the ridge, so the bandwidth figure (q, k, v, o / their gradients, bf16) is the roofline that actually bounds them.
     line["attention"] = att
-    if not args.no_cpu_baseline:
-        sample = args.cpu_clips or max(1, min(B, int(2.5e11 / fl) or 1))
-        cps, dt, cores = time_oracle(w, sample, 2, 1)
+    if extras:
+        cfgs = {}
+        for key, (wx, gb, scaling, rx) in extras.items():
+            gx, ach, _, tot, attx, sh = summarize_kernels(wx, rx, peaks)
+            flx = flops_per_clip(wx)
+            vx = gb / (rx["ms"] * 1e-3)
+            dom = next(iter(sh)) if sh else None
+            cfgs[key] = {"workload": wx["desc"], "scaling": scaling, "clips_per_gpu": wx["batch"], "global_batch": gb,
+                         "value": round(vx, 1), "unit": "clips/s", "ms_per_step": round(rx["ms"], 3),
+                         "e2e": {"value": round(gb / (rx["ms_e2e"] * 1e-3), 1), "ms_per_step": round(rx["ms_e2e"], 3),
+                                 "h2d_bytes_per_step": rx["h2d_bytes"], "d2h_bytes_per_step": 4},
+                         "gpu_launches": rx["launches"], "launch_mode": "cuda graph" if rx["graph"] else "eager",
+                         "model_tflops": round(vx / world * flx / 1e12, 1), "model_frac_of_peak": round(vx / world * flx / 1e12 / peak_tf, 4),
+                         "dominant_kernel": dom, "kernel_time_shares": sh,
+                         "roofline": {"kernel": "tvt::gemm::gemm_kernel (tcgen05)", "bound": "tensor", "achieved": round(ach, 1), "peak": peak_tf,
+                                      "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4)},
+                         "attention": attx}
+        line["configs"] = cfgs
+    if world == 1 and not args.no_extras:
+        # the library path on the same GPU (stock PyTorch: cuBLAS + ATen SDPA / LayerNorm + fused AdamW under bf16 autocast)
+        try:
+            cps, ms_t = time_torch_gpu(w, B, dev)
+            line["gpu_library_baseline"] = {"value": round(cps, 1), "unit": "clips/s", "ms_per_step": round(ms_t, 3),
+                                            "what": f"oracle/param.py modules on the same GPU under torch.autocast(bf16), fused AdamW, torch {torch.__version__}; "
+                                                    "5 timed steps after 3 warm-up, same workload and batch",
+                                            "tvt_over_library": round(value / cps, 3)}
+        except Exception as e:      # informational: never fail the bench line for it
+            line["gpu_library_baseline"] = {"unavailable": repr(e)[:200]}
+    if not args.no_cpu_baseline and world == 1:
+        # rank 0 at N = 1 only (at N > 1 the other ranks would sit in a barrier while the host runs the oracle)
+        sample = args.cpu_clips or max(1, min(B, int(1.2e12 / fl) or 1))
+        cps, dt, cores = time_oracle(w, sample, 3, 1)
         line["cpu_baseline"] = {"value": round(cps, 3), "unit": "clips/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} clips/step x 2 steps of the same workload (oracle/param.py on torch CPU, fp32)"}
+                                "sample": f"{sample} clips/step x 3 steps (+1 warm-up) of the same workload (oracle/param.py on torch CPU, fp32), "
+                                          f"{dt * 3:.1f} s of CPU work"}
     if args.breakdown:
+        breakdown = r["breakdown"]
         with open(args.breakdown, "w") as f:
             f.write(f"# per-kernel CUDA-event breakdown of one instrumented step ({w['desc']}); ms_per_step timed = {ms:.3f}\n")
             for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"]):
                 tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] else 0.0
                 f.write(f"{k:28s} calls={v['calls']:5d}  ms={v['ms']:9.3f}  share={v['ms'] / total_ms:6.3f}  TFLOP/s={tf:8.1f}\n")
             f.write("# per launch shape (GEMM stage letters: b bias, R relu, m relu mask, d dropout, r residual, F fp32 out, L hi/lo planes)\n")
-            for (k, det), v in sorted(capi.last_profile_detail.items(), key=lambda kv: -kv[1]["ms"]):
+            for (k, det), v in sorted(r["detail"].items(), key=lambda kv: -kv[1]["ms"]):
                 if not det:
                     continue
                 tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 and v["flops"] else 0.0

@@ -97,9 +97,13 @@ class SplitArgs(C.Structure):
     _fields_ = [("x", vp), ("hi", vp), ("lo", vp), ("n", i64)]
 
 
+class Split3Args(C.Structure):
+    _fields_ = [("x", vp), ("hi4", vp), ("lo4", vp), ("rows", i64), ("cols", i64), ("ld", i64), ("operand", i32), ("reserved", i32)]
+
+
 class BiasActArgs(C.Structure):
     _fields_ = [("x", vp), ("bias", vp), ("y", vp), ("rows", i64), ("cols", i64), ("out_dtype", i32), ("act", i32),
-                ("dropout_p", f32), ("dropout_seed", u64)]
+                ("dropout_p", f32), ("dropout_seed", u64), ("residual", vp), ("preact", vp)]
 
 
 class PosencArgs(C.Structure):
@@ -157,6 +161,7 @@ ENTRY_POINTS = {
     "tvt_pyramid_head": PyramidHeadArgs,
     "tvt_colsum": ColsumArgs,
     "tvt_split_f32": SplitArgs,
+    "tvt_split_f32x3": Split3Args,
     "tvt_bias_act_fwd": BiasActArgs,
     "tvt_posenc_fwd": PosencArgs,
     "tvt_act_bwd": ActBwdArgs,

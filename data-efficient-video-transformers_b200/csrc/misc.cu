@@ -39,6 +39,44 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* x, float* out, lon
 }
 
 // ---------------------------------------------------------------- split
+// Three-plane split for the EXACT forward GEMMs of the fp32 parity mode: x = x0 + x1 + x2 with bf16 planes captures all 24
+// mantissa bits, and the six products of order <= 2 (x0w0 + x0w1 + x1w0 + x0w2 + x2w0 + x1w1) reproduce an fp32 GEMM to
+// ~2^-24.  They are obtained from the ordinary 3-pass kernel (a*b + a*b_lo + a_lo*b) by concatenating along K:
+//   A  = [x0 | x0 | x2 | x1],  A_lo = [x1 | 0 | 0 | 0];   B = [w0 | w2 | w0 | w1],  B_lo = [w1 | 0 | 0 | 0]   (K' = 4K).
+// Why it matters: with two planes (2^-17) a pre-activation within ~1e-5 of zero can land on the other side of a ReLU, and
+// ONE flipped gate in a sparsely driven layer (only the CLS rows carry gradient behind the read-out) is a > 1e-3
+// relative error of that layer's weight gradient.
+__global__ void __launch_bounds__(256) split3_kernel(const float* x, __nv_bfloat16* hi4, __nv_bfloat16* lo4, long long rows, long long cols,
+                                                      long long ld, int operand) {
+  const long long vpr = cols / 8, total = rows * vpr;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / vpr, c = (idx - r * vpr) * 8;
+    const float* src = x + r * ld + c;
+    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float p0[8], p1[8], p2[8], z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p0[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+      const float r1 = v[j] - p0[j];                           // exact
+      p1[j] = __bfloat162float(__float2bfloat16_rn(r1));
+      p2[j] = r1 - p1[j];                                      // exact; rounded to bf16 by the store
+      z[j] = 0.0f;
+    }
+    __nv_bfloat16* h = hi4 + r * 4 * cols + c;
+    __nv_bfloat16* l = lo4 + r * 4 * cols + c;
+    Vec16<__nv_bfloat16>::store(h, p0);
+    Vec16<__nv_bfloat16>::store(h + cols, operand == 0 ? p0 : p2);
+    Vec16<__nv_bfloat16>::store(h + 2 * cols, operand == 0 ? p2 : p0);
+    Vec16<__nv_bfloat16>::store(h + 3 * cols, p1);
+    Vec16<__nv_bfloat16>::store(l, p1);
+    Vec16<__nv_bfloat16>::store(l + cols, z);
+    Vec16<__nv_bfloat16>::store(l + 2 * cols, z);
+    Vec16<__nv_bfloat16>::store(l + 3 * cols, z);
+  }
+}
+
 __global__ void __launch_bounds__(256) split_kernel(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n; i += stride) {
@@ -60,10 +98,13 @@ __global__ void __launch_bounds__(256) split_kernel(const float* x, __nv_bfloat1
   }
 }
 
-// ---------------------------------------------------------------- bias + act (+dropout)
+// ---------------------------------------------------------------- bias + act (+dropout) (+residual)
+// y = dropout(act(x + bias)) + residual, optional pre-activation store: the epilogue of a split-K GEMM (whose partial sums
+// met in fp32 atomics and could not apply it) — Reasoning's skinny first layer, and every forward GEMM of the fp32 parity mode
+// (short tensor-core accumulation chains, see ops.Mode.linear_fwd).
 template <typename T>
-__global__ void __launch_bounds__(256) bias_act_kernel(const float* x, const float* bias, T* y, long long rows, long long cols, int act,
-                                                       float dscale, unsigned thr16, unsigned long long seed) {
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* x, const float* bias, T* y, const T* residual, T* preact, long long rows,
+                                                       long long cols, int act, float dscale, unsigned thr16, unsigned long long seed) {
   const long long n = rows * cols;
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
@@ -74,9 +115,11 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* x, const flo
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (bias) v[j] += bias[c + j];
+      if (preact) preact[i + j] = Elem<T>::from_f(v[j]);
       if (act == TVT_ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
       else if (act == TVT_ACT_GELU) v[j] = gelu_f(v[j]);
       if (thr16) v[j] = dropout_keep_lane(bits, j, thr16) ? v[j] * dscale : 0.0f;
+      if (residual) v[j] += Elem<T>::to_f(residual[i + j]);
       y[i + j] = Elem<T>::from_f(v[j]);
     }
   }
@@ -351,6 +394,21 @@ extern "C" int tvt_split_f32(const tvt_split_args* a, void* stream) {
   return check_launch("tvt_split_f32");
 }
 
+extern "C" int tvt_split_f32x3(const tvt_split3_args* a, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(a != nullptr && a->x && a->hi4 && a->lo4, "tvt_split_f32x3: null pointer");
+  TVT_REQUIRE(a->rows > 0 && a->cols > 0 && a->cols % 8 == 0, "tvt_split_f32x3: cols must be a positive multiple of 8");
+  TVT_REQUIRE(a->ld >= a->cols, "tvt_split_f32x3: ld smaller than cols");
+  TVT_REQUIRE(a->operand == 0 || a->operand == 1, "tvt_split_f32x3: operand must be 0 (A) or 1 (B)");
+  TVT_REQUIRE(al16(a->x) && al16(a->hi4) && al16(a->lo4) && a->ld % 4 == 0, "tvt_split_f32x3: pointers / pitch must keep 16-byte alignment");
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  const long long vecs = a->rows * (a->cols / 8);
+  misc::split3_kernel<<<misc::grid1d(vecs, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a->x, (__nv_bfloat16*)a->hi4, (__nv_bfloat16*)a->lo4, a->rows, a->cols, a->ld, a->operand);
+  return check_launch("tvt_split_f32x3");
+}
+
 extern "C" int tvt_bias_act_fwd(const tvt_bias_act_args* a, void* stream) {
   using namespace tvt;
   TVT_REQUIRE(a != nullptr && a->x && a->y, "tvt_bias_act_fwd: null pointer");
@@ -366,8 +424,8 @@ extern "C" int tvt_bias_act_fwd(const tvt_bias_act_args* a, void* stream) {
   if (a->dropout_p > 0.0f) { thr = (unsigned)(a->dropout_p * 65536.0f + 0.5f); sc = 65536.0f / (65536.0f - (float)thr); }
   const long long n4 = a->rows * a->cols / 4;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->out_dtype == TVT_F32) misc::bias_act_kernel<float><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (float*)a->y, a->rows, a->cols, a->act, sc, thr, a->dropout_seed);
-  else misc::bias_act_kernel<__nv_bfloat16><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (__nv_bfloat16*)a->y, a->rows, a->cols, a->act, sc, thr, a->dropout_seed);
+  if (a->out_dtype == TVT_F32) misc::bias_act_kernel<float><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (float*)a->y, (const float*)a->residual, (float*)a->preact, a->rows, a->cols, a->act, sc, thr, a->dropout_seed);
+  else misc::bias_act_kernel<__nv_bfloat16><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (__nv_bfloat16*)a->y, (const __nv_bfloat16*)a->residual, (__nv_bfloat16*)a->preact, a->rows, a->cols, a->act, sc, thr, a->dropout_seed);
   return check_launch("tvt_bias_act_fwd");
 }
 

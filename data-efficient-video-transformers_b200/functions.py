@@ -91,7 +91,7 @@ class EncoderLayerFn(torch.autograd.Function):
         hd, Sq, ff = d // H, n // B, l1_w.shape[0]
         p = cfg.p
         seeds = [next_seed() for _ in range(4)] if p > 0 else [0, 0, 0, 0]
-        xp = m.split(x)
+        xp = m.fwd_planes(x)
         if mem is None:
             qkv = m.linear_fwd(xp, n, d, in_w, in_b)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
@@ -99,19 +99,19 @@ class EncoderLayerFn(torch.autograd.Function):
         else:
             nk = mem.shape[0]
             Sk = nk // B
-            memp = m.split(mem)
+            memp = m.fwd_planes(mem)
             qkv = m.linear_fwd(xp, n, d, in_w, in_b[:d], rows=(0, d))                 # q
             kv = m.linear_fwd(memp, nk, d, in_w, in_b[d:], rows=(d, 3 * d))          # [nk, 2d]
             q, k, v = qkv, kv[:, :d], kv[:, d:]
         scale = 1.0 / math.sqrt(hd)
         attn, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, hd, scale, dropout_p=p, seed=seeds[0], impl=cfg.attn_impl)
-        attnp = m.split(attn)
+        attnp = m.fwd_planes(attn)
         y1 = m.linear_fwd(attnp, n, d, out_w, out_b, residual=x, dropout_p=p, seed=seeds[1])
         x1, mean1, rstd1 = ops.layernorm_fwd(y1, n1_w, n1_b)
-        x1p = m.split(x1)
+        x1p = m.fwd_planes(x1)
         z = m.empty(n, ff, device=x.device) if cfg.act == ACT_GELU else None
         h = m.linear_fwd(x1p, n, d, l1_w, l1_b, act=cfg.act, dropout_p=p, seed=seeds[2], preact=z)
-        hp = m.split(h)
+        hp = m.fwd_planes(h)
         y2 = m.linear_fwd(hp, n, ff, l2_w, l2_b, residual=x1, dropout_p=p, seed=seeds[3])
         out, mean2, rstd2 = ops.layernorm_fwd(y2, n2_w, n2_b)
         ctx.cfg, ctx.seeds, ctx.dims = cfg, seeds, (n, d, B, H, hd, Sq, Sk, ff)
@@ -212,18 +212,18 @@ class PreNormLayerFn(torch.autograd.Function):
         p = cfg.p
         seeds = [next_seed() for _ in range(3)] if p > 0 else [0, 0, 0]
         xn, mean1, rstd1 = ops.layernorm_fwd(x, n1_w, n1_b)
-        qkv = m.linear_fwd(m.split(xn), n, d, qkv_w, None)
+        qkv = m.linear_fwd(m.fwd_planes(xn), n, d, qkv_w, None)
         scale = dim_head ** -0.5
         attn, lse = ops.attention_fwd(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], B, H, S, S, dim_head, scale,
                                       impl=cfg.attn_impl)
         if out_w is not None:
-            x1 = m.linear_fwd(m.split(attn), n, inner, out_w, out_b, residual=x, dropout_p=p, seed=seeds[0])
+            x1 = m.linear_fwd(m.fwd_planes(attn), n, inner, out_w, out_b, residual=x, dropout_p=p, seed=seeds[0])
         else:   # heads == 1 and dim_head == dim: no output projection, no dropout (vit.py:41-44)
             x1 = attn + x
         xn2, mean2, rstd2 = ops.layernorm_fwd(x1, n2_w, n2_b)
         z = m.empty(n, ff, device=x.device)
-        h = m.linear_fwd(m.split(xn2), n, d, l1_w, l1_b, act=ACT_GELU, dropout_p=p, seed=seeds[1], preact=z)
-        out = m.linear_fwd(m.split(h), n, ff, l2_w, l2_b, residual=x1, dropout_p=p, seed=seeds[2])
+        h = m.linear_fwd(m.fwd_planes(xn2), n, d, l1_w, l1_b, act=ACT_GELU, dropout_p=p, seed=seeds[1], preact=z)
+        out = m.linear_fwd(m.fwd_planes(h), n, ff, l2_w, l2_b, residual=x1, dropout_p=p, seed=seeds[2])
         ctx.cfg, ctx.seeds, ctx.dims = cfg, seeds, (n, d, B, H, dim_head, S, inner, ff)
         ctx.has_out = out_w is not None
         ctx.save_for_backward(x, xn, mean1, rstd1, qkv, attn, lse, x1, xn2, mean2, rstd2, z, h,
@@ -328,7 +328,7 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mode, x, w, b):
         M, K = x.shape
-        xp = mode.split(x)
+        xp = mode.fwd_planes(x)
         y = mode.linear_fwd(xp, M, K, w, b)
         ctx.mode = mode
         ctx.params = (w, b)
@@ -372,15 +372,18 @@ class MlpFn(torch.autograd.Function):
             p = drops[i]
             seed = next_seed() if p > 0 else 0
             seeds.append(seed)
-            curp = mode.split(cur)
+            curp = mode.fwd_planes(cur)
             z = mode.empty(M, N, device=x.device) if acts[i] == ACT_GELU else None
             tiles = ((M + 127) // 128) * ((N + 127) // 128)
             kb = (K + 63) // 64
             if tiles * 4 <= ops.num_sms() and kb >= 16:
-                wh, wl = mode.weight(ws[i])
+                exact = getattr(curp, "exact", False)
+                wh, wl = mode.weight_exact(ws[i]) if exact else mode.weight(ws[i])
+                Kx = 4 * K if exact else K
                 acc = torch.zeros(M, N, dtype=torch.float32, device=x.device)
-                splits = max(2, ops.pick_splits(((M + 127) // 128) * ((N + 255) // 256), kb, 64))
-                ops.gemm(curp[0], wh, M, N, K, a_lo=curp[1], b_lo=wl, out_f32=acc, splits=splits, atomic=True)
+                splits = (ops.exact_splits(Kx) if exact else
+                          max(2, ops.pick_splits(((M + 127) // 128) * ((N + 255) // 256), (Kx + 63) // 64, 64)))
+                ops.gemm(curp[0], wh, M, N, Kx, a_lo=curp[1], b_lo=wl, out_f32=acc, splits=splits, atomic=True)
                 if z is not None:
                     ops.bias_act(acc, bs[i], z, ACT_NONE)
                 y = mode.empty(M, N, device=x.device)

@@ -87,6 +87,29 @@ def split_f32(x, hi, lo=None):
     capi.call("tvt_split_f32", s, _stream())
 
 
+def split_f32x3(x, operand):
+    """x fp32 [rows, cols] (row pitch x.stride(0)) -> (hi4, lo4) bf16 [rows, 4 * cols]: the K-concatenated three-plane
+    layout of tvt_split_f32x3 (operand 0 = activation / A side, 1 = weight / B side)."""
+    _cuda(x)
+    rows, cols = x.shape
+    hi4 = torch.empty(rows, 4 * cols, dtype=torch.bfloat16, device=x.device)
+    lo4 = torch.empty_like(hi4)
+    a = capi.Split3Args(_p(x), _p(hi4), _p(lo4), rows, cols, _rowmajor(x), operand, 0)
+    capi.call("tvt_split_f32x3", a, _stream())
+    return hi4, lo4
+
+
+def exact_splits(k_total):
+    """Split-K factor that keeps every tensor-core accumulation chain of an exact fp32-mode GEMM at <= 2 k-blocks of 64."""
+    kb = (k_total + 63) // 64
+    return max(1, (kb + 1) // 2)
+
+
+class ExactPlanes(tuple):
+    """(hi4, lo4) forward operand of the fp32 mode's exact GEMMs (see Mode.fwd_planes)."""
+    exact = True
+
+
 def colsum(x, out):
     """out[c] += sum_r x[r, c]; out fp32, zero-filled by the caller."""
     _cuda(x, out)
@@ -94,9 +117,14 @@ def colsum(x, out):
     capi.call("tvt_colsum", a, _stream())
 
 
-def bias_act(x, bias, out, act=ACT_NONE, dropout_p=0.0, seed=0):
-    _cuda(x, bias, out)
-    a = capi.BiasActArgs(_p(x), _p(bias), _p(out), x.shape[0], x.shape[1], _dt(out), act, dropout_p, seed)
+def bias_act(x, bias, out, act=ACT_NONE, dropout_p=0.0, seed=0, residual=None, preact=None):
+    """out = dropout(act(x + bias)) (+ residual); ``preact`` receives x + bias.  x fp32 [rows, cols] contiguous; residual /
+    preact contiguous tensors of out's dtype."""
+    _cuda(x, bias, out, residual, preact)
+    for t in (residual, preact):
+        if t is not None and (t.dtype != out.dtype or not t.is_contiguous()):
+            raise TvtError("bias_act: residual / preact must be contiguous tensors of the output dtype")
+    a = capi.BiasActArgs(_p(x), _p(bias), _p(out), x.shape[0], x.shape[1], _dt(out), act, dropout_p, seed, _p(residual), _p(preact))
     capi.call("tvt_bias_act_fwd", a, _stream())
 
 
@@ -153,6 +181,33 @@ class Mode:
         split_f32(x.contiguous(), hi, lo)
         return hi, lo
 
+    def fwd_planes(self, x):
+        """Operand planes of a FORWARD GEMM.  bf16 mode: the activation itself.  fp32 mode: the three-plane K-concatenated
+        layout, so that pre-activations carry fp32 accuracy (2^-24, not the 2^-17 of two planes) and no ReLU / GELU gate
+        lands on the wrong side of zero relative to an fp32 reference; the backward GEMMs (dgrad / wgrad), whose errors
+        are not amplified by a gate, keep the two-plane 3-pass form."""
+        if not self.fp32:
+            return self.split(x)
+        if x.dim() != 2 or x.shape[1] % 8 != 0 or x.stride(1) != 1 or x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0:
+            return self.split(x)
+        return ExactPlanes(split_f32x3(x, 0))
+
+    def weight_exact(self, w, rows=None):
+        """fp32 master weight [N, K] -> cached (hi4, lo4) [N, 4K] planes of the exact forward GEMMs (see fwd_planes)."""
+        key = (id(w), "x3")
+        ent = self._wcache.get(key)
+        if ent is None or ent[0]() is not w or ent[1] != w._version:
+            wd = w.detach()
+            if wd.dtype != torch.float32:
+                raise TvtError("master weights must be fp32")
+            hi4, lo4 = split_f32x3(wd.contiguous(), 1)
+            ent = (weakref.ref(w), w._version, hi4, lo4)
+            self._wcache[key] = ent
+        hi, lo = ent[2], ent[3]
+        if rows is not None:
+            hi, lo = hi[rows[0]:rows[1]], lo[rows[0]:rows[1]]
+        return hi, lo
+
     def weight(self, w, rows=None):
         """fp32 master weight [N, K] -> cached (hi, lo) bf16 planes, refreshed when the parameter changes
         (version counter) — one conversion per optimizer step.  ``rows=(r0, r1)`` selects a row slice
@@ -179,6 +234,25 @@ class Mode:
     # y[M,N] = act(x W^T + b) (+dropout) (+residual)
     def linear_fwd(self, xp, M, K, W, b, *, act=ACT_NONE, residual=None, dropout_p=0.0, seed=0, preact=None,
                    rows=None):
+        if getattr(xp, "exact", False):
+            # fp32 parity mode: three-plane operands (all 24 mantissa bits) AND short tensor-core accumulation chains.  The
+            # fp32 accumulator in TMEM truncates when it aligns each MMA's products, a small BIASED error per instruction
+            # that grows linearly with the chain (measured, tools/diag_gemm_precision.py: 1.7e-5 over K = 2048 in one chain
+            # vs 2.8e-7 in chains of two 64-wide k-blocks, cuBLAS fp32: 2.9e-7), so the contraction is split into chains of
+            # at most two k-blocks whose partial sums meet in fp32 atomics, and the epilogue runs as its own kernel.
+            if W.shape[1] % 8 != 0:
+                raise TvtError("exact forward planes need K % 8 == 0")
+            wh, wl = self.weight_exact(W, rows)
+            N = wh.shape[0]
+            Kx = 4 * K
+            acc = torch.zeros(M, N, dtype=torch.float32, device=xp[0].device)
+            gemm(xp[0], wh, M, N, Kx, a_lo=xp[1], b_lo=wl, lda=_rowmajor(xp[0]), ldb=Kx, out_f32=acc,
+                 splits=exact_splits(Kx), atomic=True)
+            y = self.empty(M, N, device=xp[0].device)
+            if residual is not None and not residual.is_contiguous():
+                residual = residual.contiguous()
+            bias_act(acc, b, y, act, dropout_p, seed, residual=residual, preact=preact)
+            return y
         wh, wl = self.weight(W, rows)
         N = wh.shape[0]
         y = self.empty(M, N, device=xp[0].device)

@@ -319,7 +319,21 @@ typedef struct {
 } tvt_split_args;
 TVT_API int tvt_split_f32(const tvt_split_args* args, void* stream);
 
-/* y = act(x + bias) (+ dropout) elementwise over [rows, cols] fp32 input -> T output (after a split-K
+/* Three-plane split for the exact forward GEMMs of the fp32 parity mode: x [rows, cols] (row pitch ld) = x0 + x1 + x2
+ * (bf16 planes, all 24 mantissa bits) laid out so that ONE 3-pass tvt_gemm over K' = 4 * cols computes every product of
+ * order <= 2:  operand 0 (A):  hi4 = [x0 | x0 | x2 | x1], lo4 = [x1 | 0 | 0 | 0];
+ *              operand 1 (B):  hi4 = [w0 | w2 | w0 | w1], lo4 = [w1 | 0 | 0 | 0];  both [rows, 4 * cols] bf16. */
+typedef struct {
+  const float* x;
+  void* hi4;
+  void* lo4;
+  int64_t rows, cols, ld;
+  int32_t operand;
+  int32_t reserved;
+} tvt_split3_args;
+TVT_API int tvt_split_f32x3(const tvt_split3_args* args, void* stream);
+
+/* y = dropout(act(x + bias)) (+ residual) elementwise over [rows, cols] fp32 input -> T output (after a split-K
  * GEMM whose epilogue cannot apply them), and its backward dx = dy * act'(y) (* dropout mask). */
 typedef struct {
   const float* x;
@@ -330,6 +344,8 @@ typedef struct {
   int32_t act;
   float dropout_p;
   uint64_t dropout_seed;
+  const void* residual; /* optional [rows, cols] of out_dtype, added after the dropout */
+  void* preact;         /* optional [rows, cols] of out_dtype: x + bias before the activation (GELU backward) */
 } tvt_bias_act_args;
 TVT_API int tvt_bias_act_fwd(const tvt_bias_act_args* args, void* stream);
 

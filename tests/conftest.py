@@ -36,6 +36,8 @@ def _parity_case(request):
     import util
     if "gpu" in request.keywords:
         util.CURRENT_CASE[0] = request.node.name[5:] if request.node.name.startswith("test_") else request.node.name
+        if request.node.fspath.basename == "test_kernels_gpu.py":
+            util.KERNEL_CASES.add(util.CURRENT_CASE[0].split("[")[0])
     yield
     util.CURRENT_CASE[0] = None
 

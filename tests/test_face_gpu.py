@@ -36,8 +36,8 @@ def _no_dropout(*mods):
 
 
 def _ac(fn):
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        return fn()
+    import util
+    return util.reduced(fn)
 
 
 def _targets(B, C, gen):
@@ -79,17 +79,17 @@ def test_frame_transformer_modes_parity(api, model, precision):
     else:
         assert_close(out, out_r, TOL[precision], "logits")
     assert_close(loss, loss_r, TOL[precision], "loss")
-    yard = None
-    if precision == "bf16":
-        yard = copy.deepcopy(ref)
-        yard.zero_grad(set_to_none=True)
+    import util
+    yard = copy.deepcopy(ref)
+    yard.zero_grad(set_to_none=True)
+    util.YARD_PRECISION[0] = precision
 
-        def run(m):
-            if model == "distil":
-                s, t = _ac(lambda: m(img, vid))
-                return m.criterion(s.float(), y) + m.distil_criterion(s.float(), torch.argmax(t.float(), dim=-1))
-            return m.criterion(_ac(lambda: m(img, vid)).float(), y)
-        run(yard).backward()
+    def run(m):
+        if model == "distil":
+            s, t = _ac(lambda: m(img, vid))
+            return m.criterion(s.float(), y) + m.distil_criterion(s.float(), torch.argmax(t.float(), dim=-1))
+        return m.criterion(_ac(lambda: m(img, vid)).float(), y)
+    run(yard).backward()
     worst = grads_close(mod, ref, TOL[precision], f"{model} ", yard=yard)
     print("FrameTransformer", model, precision, "worst grad", worst)
     # evaluation hooks feed the callbacks' side channel (frame_transformer.py:331-333,364-366)
@@ -194,11 +194,11 @@ def test_vivit_parity(api, precision):
     out = mod(x)
     (out * w).sum().backward()
     assert_close(out, ref(x.clone()), TOL[precision], "ViViT logits")
-    yard = None
-    if precision == "bf16":
-        yard = copy.deepcopy(ref)
-        yard.zero_grad(set_to_none=True)
-        (_ac(lambda: yard(x.clone())).float() * w).sum().backward()
+    import util
+    yard = copy.deepcopy(ref)
+    yard.zero_grad(set_to_none=True)
+    util.YARD_PRECISION[0] = precision
+    (_ac(lambda: yard(x.clone())).float() * w).sum().backward()
     grads_close(mod, ref, TOL[precision], "vivit ", yard=yard)
 
 

@@ -15,10 +15,15 @@ NOTES = []
 # set by conftest's autouse fixture for gpu-marked tests: the default `case` of assert_close / grads_close
 CURRENT_CASE = [None]
 
-# The only parameters that may use the yardstick clause (bf16 mode): ReLU-gated FFN-in gradients (gate flips of
-# near-zero pre-activations) and per-batch-slot CLS rows (single-token gradients, no averaging over tokens).
-# Anything else exceeding the tolerance fails outright, whatever stock PyTorch bf16 does.
-EXEMPTIBLE = ("linear1.", "cls")
+# The only parameters that may use the yardstick clause, by class (every use is listed in the parity report):
+#   "linear1.", "reason.relation."  ReLU-gated layers (encoder FFN-in, the pyramid's relation MLPs): a pre-activation within
+#                                   rounding distance of zero lands on the other side of the gate, and one flipped gate is a
+#                                   finite error of that layer's weight / bias gradient;
+#   "cls"                           per-batch-slot CLS rows: single-token gradients, no averaging over tokens;
+#   "expert_encoder."               the input projection of a memory stream (its only gradient path is the cross-attention
+#                                   softmax over the other modality: small, cancellation-prone sums).
+# Anything else exceeding the tolerance fails outright, whatever stock PyTorch does.
+EXEMPTIBLE = ("linear1.", "reason.relation.", "cls", "expert_encoder.")
 
 
 def _record(case, what, err, tol, yard=None, exempt=False, limit=None):
@@ -28,6 +33,40 @@ def _record(case, what, err, tol, yard=None, exempt=False, limit=None):
     REPORT.append({"case": case, "what": what, "err": float(err), "tol": float(tol),
                    "yardstick_err": None if yard is None else float(yard), "exempt": bool(exempt),
                    "limit": float(tol if limit is None else limit)})
+
+
+class stock_reduced_precision:
+    """Context for the YARDSTICK run of the fp32 oracle: what stock PyTorch gives in the reduced-precision mode that
+    corresponds to the tvt mode under test — ``torch.autocast(bf16)`` for the bf16 mode, TF32 tensor-core matmuls
+    (``allow_tf32``: the library's own "fp32 data, tensor cores, fp32 accumulate" mode) for the fp32-accumulate mode."""
+
+    def __init__(self, precision):
+        self.precision = precision
+
+    def __enter__(self):
+        if self.precision == "bf16":
+            self.ctx = torch.autocast("cuda", dtype=torch.bfloat16)
+            self.ctx.__enter__()
+        else:
+            self.saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.precision == "bf16":
+            return self.ctx.__exit__(*exc)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.saved
+        return False
+
+
+YARD_PRECISION = ["bf16"]      # which reduced-precision mode `reduced(fn)` runs under (set by the tests' _yardstick helpers)
+
+
+def reduced(fn):
+    """Run a forward under the stock reduced-precision mode of the case being checked (losses are evaluated outside)."""
+    with stock_reduced_precision(YARD_PRECISION[0]):
+        return fn()
 
 
 def rel_err(a, b):
@@ -54,10 +93,11 @@ def copy_state(dst, src):
 def grads_close(mod, ref, tol, what="", skip=(), yard=None, slack=1.5, case=None, exemptible=EXEMPTIBLE):
     """Every parameter gradient of `mod` matches `ref`'s within normwise tolerance `tol`.
 
-    `yard` (optional) is a copy of the fp32 oracle whose gradients were computed under stock
-    torch.autocast(bf16): a parameter whose name contains one of `exemptible` may exceed `tol` only if stock
-    PyTorch bf16 does so too, and then by at most `slack` x the yardstick's own error (ReLU-gate flips and
-    single-token CLS rows are inherently noisy in bf16 for any implementation).  Every comparison is recorded
+    `yard` (optional) is a copy of the fp32 oracle whose gradients were computed by stock PyTorch in the matching
+    reduced-precision mode (`stock_reduced_precision`: autocast(bf16) for the bf16 mode, TF32 matmuls for the
+    fp32-accumulate mode): a parameter whose name contains one of `exemptible` may exceed `tol` only if stock
+    PyTorch does so too, and then by at most `slack` x the yardstick's own error (a single flipped ReLU gate and
+    single-token CLS rows are inherently noisy below true-fp32 precision for any implementation).  Every comparison is recorded
     under `case` for the parity report.  Returns (worst name, worst error, number of yardstick exemptions)."""
     rp = dict(ref.named_parameters())
     yp = dict(yard.named_parameters()) if yard is not None else {}
@@ -87,9 +127,13 @@ def grads_close(mod, ref, tol, what="", skip=(), yard=None, slack=1.5, case=None
         _record(case, "grad " + name, e, tol, ye, used, limit)
         if e > limit:
             failures.append(f"{what}{name}: gradient relative error {e:.3e} > {limit:.1e}"
-                            + (f" (stock bf16 yardstick {ye:.3e})" if ye is not None else ""))
+                            + (f" (stock yardstick {ye:.3e})" if ye is not None else ""))
     assert not failures, "; ".join(failures)
     return worst[0], worst[1], exempt
+
+
+# module-level tests are summarised on the terminal; the single-kernel tests of tests/test_kernels_gpu.py only in the JSON
+KERNEL_CASES = set()
 
 
 def summarize():
@@ -99,6 +143,8 @@ def summarize():
         cases.setdefault(r["case"], []).append(r)
     lines = []
     for case, rows in cases.items():
+        if case.split("[")[0] in KERNEL_CASES:
+            continue                          # single-kernel checks: in the JSON table only
         grads = [r for r in rows if r["what"].startswith("grad ")]
         other = [r for r in rows if not r["what"].startswith("grad ")]
         ex = [r for r in grads if r["exempt"]]
@@ -111,7 +157,7 @@ def summarize():
                          f"{len(ex)} yardstick exemptions")
             if ex:
                 wr = max(ex, key=lambda r: r["err"] / max(r["yardstick_err"], 1e-30))
-                parts.append(f"worst exempt ratio {wr['err'] / max(wr['yardstick_err'], 1e-30):.2f}x stock-bf16 "
+                parts.append(f"worst exempt ratio {wr['err'] / max(wr['yardstick_err'], 1e-30):.2f}x stock "
                              f"({wr['what'][5:]}: {wr['err']:.2e} vs {wr['yardstick_err']:.2e})")
         lines.append(" ".join(parts))
     return lines
