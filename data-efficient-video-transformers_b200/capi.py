@@ -118,7 +118,8 @@ class ActBwdArgs(C.Structure):
 
 class OptimStepArgs(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("p_hi", vp), ("p_lo", vp), ("n", i64), ("kind", i32), ("step", i32),
-                ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("momentum", f32), ("grad_scale", f32)]
+                ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("momentum", f32), ("grad_scale", f32),
+                ("step_dev", vp)]
 
 
 class HeadLinearFwdArgs(C.Structure):
@@ -172,7 +173,7 @@ ENTRY_POINTS = {
     "tvt_eval_readout": EvalReadoutArgs,
     "tvt_feature_augment": FeatureAugmentArgs,
 }
-PLAIN_SYMBOLS = ("tvt_last_error", "tvt_version", "tvt_device_check")
+PLAIN_SYMBOLS = ("tvt_last_error", "tvt_version", "tvt_device_check", "tvt_set_seed_source", "tvt_step_counter_advance")
 
 _lib = None
 launches = 0  # number of kernel-launching entry-point calls made through this module (bench.py reads it)
@@ -191,6 +192,10 @@ def load():
     lib.tvt_last_error.argtypes = []
     lib.tvt_version.restype = C.c_int
     lib.tvt_device_check.restype = C.c_int
+    lib.tvt_set_seed_source.restype = C.c_int
+    lib.tvt_set_seed_source.argtypes = [vp]
+    lib.tvt_step_counter_advance.restype = C.c_int
+    lib.tvt_step_counter_advance.argtypes = [vp, C.c_int, vp]
     for name, st in ENTRY_POINTS.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -246,6 +251,21 @@ def call(name, args, stream):
         _profile.append((name, e0, e1, _flops(name, args), _detail(name, args)))
     if rc != 0:
         raise TvtError(f"{name} failed with status {rc}: {last_error()}")
+    launches += 1
+
+
+def set_seed_source(device_ptr):
+    """Register (or clear, with None / 0) the device-resident step counter folded into every dropout seed."""
+    rc = load().tvt_set_seed_source(vp(device_ptr or 0))
+    if rc != 0:
+        raise TvtError(f"tvt_set_seed_source failed with status {rc}: {last_error()}")
+
+
+def step_counter_advance(device_ptr, count, stream):
+    global launches
+    rc = load().tvt_step_counter_advance(vp(device_ptr), int(count), vp(stream))
+    if rc != 0:
+        raise TvtError(f"tvt_step_counter_advance failed with status {rc}: {last_error()}")
     launches += 1
 
 

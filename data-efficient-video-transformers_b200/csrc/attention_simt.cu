@@ -17,7 +17,7 @@ struct Params {
   int B, H, Sq, Sk, hd;
   long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
   float scale;
-  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed; const unsigned long long* seed_src;
 };
 
 // Stage rows [0, S) x [0, hd) of a head into smem (pitch hd + 4 floats) as fp32.
@@ -47,7 +47,7 @@ __device__ __forceinline__ float dot_row(const float* a, const float* b, int hd)
 // Dropout on attention probabilities (mask layout: tvt_common.cuh, attn_drop_bits).
 __device__ __forceinline__ float drop_mul(const Params& p, long long bh, int i, int j) {
   if (!p.dropout_thr16) return 1.0f;
-  const uint64_t bits = attn_drop_bits(p.dropout_seed, attn_rowkey(bh, p.Sq, p.Sk, i), j >> 2);
+  const uint64_t bits = attn_drop_bits(mix_seed(p.dropout_seed, p.seed_src), attn_rowkey(bh, p.Sq, p.Sk, i), j >> 2);
   return dropout_keep_lane(bits, j & 3, p.dropout_thr16) ? p.dropout_scale : 0.0f;
 }
 
@@ -280,6 +280,7 @@ extern "C" int tvt_attention_fwd(const tvt_attention_fwd_args* a, void* stream) 
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
     p.dropout_seed = a->dropout_seed;
+    p.seed_src = seed_source();
   }
   return attn_simt::launch_fwd(p, a->dtype == TVT_F32, static_cast<cudaStream_t>(stream));
 }
@@ -313,6 +314,7 @@ extern "C" int tvt_attention_bwd(const tvt_attention_bwd_args* a, void* stream) 
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
     p.dropout_seed = a->dropout_seed;
+    p.seed_src = seed_source();
   }
   return attn_simt::launch_bwd(p, a->dtype == TVT_F32, static_cast<cudaStream_t>(stream));
 }

@@ -37,7 +37,7 @@ struct Params {
   int kv_box;                 // rows per K / V TMA box (divides sk_pad)
   const __nv_bfloat16* q_in; long long ldq;   // raw Q rows for the CUDA-core tail path
   float scale;
-  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed; const unsigned long long* seed_src;
   __nv_bfloat16* o; long long ldo;
   float* lse;
   // backward
@@ -64,14 +64,14 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
 
 __device__ __forceinline__ float drop_mul(const Params& p, long long bh, int i, int j) {
   if (!p.dropout_thr16) return 1.0f;
-  const uint64_t bits = attn_drop_bits(p.dropout_seed, attn_rowkey(bh, p.Sq, p.Sk, i), j >> 2);
+  const uint64_t bits = attn_drop_bits(mix_seed(p.dropout_seed, p.seed_src), attn_rowkey(bh, p.Sq, p.Sk, i), j >> 2);
   return dropout_keep_lane(bits, j & 3, p.dropout_thr16) ? p.dropout_scale : 0.0f;
 }
 // Dropout multipliers of 16 consecutive keys [c0, c0 + 16) of one query row (c0 % 16 == 0): 4 hashes.
 __device__ __forceinline__ void drop_mul16(const Params& p, uint64_t rowkey, int c0, float (&m)[16]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const uint64_t bits = attn_drop_bits(p.dropout_seed, rowkey, (c0 >> 2) + g);
+    const uint64_t bits = attn_drop_bits(mix_seed(p.dropout_seed, p.seed_src), rowkey, (c0 >> 2) + g);
 #pragma unroll
     for (int i = 0; i < 4; ++i) m[4 * g + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? p.dropout_scale : 0.0f;
   }
@@ -1075,7 +1075,7 @@ __global__ void __launch_bounds__(kThreadsBwd2) bwd2_kernel(const __grid_constan
             }
             float m = 1.0f;
             if (p.dropout_thr16) {
-              const uint64_t bits = attn_drop_bits(p.dropout_seed, rowkey, (k0 + j) >> 2);
+              const uint64_t bits = attn_drop_bits(mix_seed(p.dropout_seed, p.seed_src), rowkey, (k0 + j) >> 2);
               m = dropout_keep_lane(bits, (k0 + j) & 3, p.dropout_thr16) ? p.dropout_scale : 0.0f;
             }
             const float prob = exp2f(sacc * sl2 - Lt);
@@ -1481,7 +1481,7 @@ __global__ void __launch_bounds__(kThreadsBwd3) bwd3_kernel(const __grid_constan
             }
             float m = 1.0f;
             if (p.dropout_thr16) {
-              const uint64_t bits = attn_drop_bits(p.dropout_seed, rowkey, j >> 2);
+              const uint64_t bits = attn_drop_bits(mix_seed(p.dropout_seed, p.seed_src), rowkey, j >> 2);
               m = dropout_keep_lane(bits, j & 3, p.dropout_thr16) ? p.dropout_scale : 0.0f;
             }
             const float prob = ex2_approx(fmaf(sacc, sl2, -Lt));
@@ -1652,6 +1652,7 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
     p.dropout_seed = a->dropout_seed;
+    p.seed_src = seed_source();
   }
   CUtensorMap tq, tk, tv;
   const long long w = a->heads * HD;
@@ -1686,6 +1687,7 @@ int launch_bwd(const tvt_attention_bwd_args* a, cudaStream_t s) {
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
     p.dropout_seed = a->dropout_seed;
+    p.seed_src = seed_source();
   }
   CUtensorMap tq, tk, tv, tdo;
   const long long w = a->heads * HD;

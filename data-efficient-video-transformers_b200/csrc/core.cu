@@ -58,7 +58,30 @@ int require_sm100() {
   return status;
 }
 
+// Device-resident step counter folded into every dropout seed (tvt_common.cuh mix_seed); nullptr = none.
+static const unsigned long long* g_seed_source = nullptr;
+const unsigned long long* seed_source() { return g_seed_source; }
+
+__global__ void step_counter_kernel(unsigned long long* ctr, int n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int i = 0; i < n; ++i) ctr[i] += 1ull;
+}
+
 }  // namespace tvt
+
+extern "C" int tvt_set_seed_source(const void* device_counter) {
+  tvt::g_seed_source = static_cast<const unsigned long long*>(device_counter);
+  return TVT_OK;
+}
+
+extern "C" int tvt_step_counter_advance(void* device_counters, int count, void* stream) {
+  using namespace tvt;
+  TVT_REQUIRE(device_counters != nullptr && count >= 1 && count <= 16, "tvt_step_counter_advance: bad arguments");
+  int rc = require_sm100();
+  if (rc != TVT_OK) return rc;
+  step_counter_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned long long*>(device_counters), count);
+  return check_launch("tvt_step_counter_advance");
+}
 
 extern "C" const char* tvt_last_error(void) { return tvt::g_err; }
 extern "C" int tvt_version(void) { return 100; }

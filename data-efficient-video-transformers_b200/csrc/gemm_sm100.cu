@@ -39,7 +39,7 @@ struct Params {
   const void* residual; int residual_f32; long long ld_residual;
   const void* relu_mask; int mask_f32; long long ld_mask;
   const void* gelu_gate; int gate_f32; long long ld_gate;
-  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed; const unsigned long long* seed_src;
   unsigned drop_rk[kDropoutRounds];   // per-round keys of the dropout hash (host-computed: they are launch constants)
   void* out_preact; int preact_f32; long long ld_preact;
   float* out_f32; long long ld_f32; int atomic_out;
@@ -192,7 +192,7 @@ __device__ __forceinline__ void epilogue_stages(const Params& p, long long row, 
     const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const uint64_t bits = dropout_bits4(p.dropout_seed, e4 + q);
+      const uint64_t bits = dropout_bits4(mix_seed(p.dropout_seed, p.seed_src), e4 + q);
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[4 * q + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? v[4 * q + i] * p.dropout_scale : 0.0f;
     }
@@ -618,7 +618,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;   // multiple of 8: + q never carries
           uint32_t out[16];
           epilogue_fast<kEpi>(p, scale, bias_addr + c * 128, static_cast<uint32_t>(e4),
-                              static_cast<uint32_t>(e4 >> 32) ^ static_cast<uint32_t>(p.dropout_seed >> 32), r, side, out);
+                              static_cast<uint32_t>(e4 >> 32) ^ static_cast<uint32_t>(mix_seed(p.dropout_seed, p.seed_src) >> 32), r, side, out);
           release_slot();
           if constexpr (side_ldg(kEpi)) {
             if (c + 1 < BN / 64 && col0 + 32 < p.N && row < p.M) { ldg256(side_row + col0 + 32, side); ldg256(side_row + col0 + 48, side + 8); }
@@ -902,6 +902,7 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
     p.dropout_seed = a->dropout_seed;
+    p.seed_src = seed_source();
     for (int r = 0; r < kDropoutRounds; ++r) p.drop_rk[r] = static_cast<unsigned>(a->dropout_seed) + r * kDropoutWeyl;
   }
   p.out_preact = a->out_preact; p.preact_f32 = a->preact_dtype == TVT_F32; p.ld_preact = a->ld_preact;

@@ -20,7 +20,7 @@ struct FwdParams {
   float* mean; float* rstd;
   long long rows; int d; int S;  // S > 0 selects embed mode (rows = B * S)
   float eps;
-  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed; const unsigned long long* seed_src;
 };
 
 template <typename T, int kChunks>
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kWarps * 32, kChunks <= 4 ? 3 : 1) ln_fwd_kern
             const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.d + col) >> 2;
 #pragma unroll
             for (int g = 0; g < V / 4; ++g) {
-              const uint64_t bits = dropout_bits4(p.dropout_seed, e4 + g);
+              const uint64_t bits = dropout_bits4(mix_seed(p.dropout_seed, p.seed_src), e4 + g);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 v[c][4 * g + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? v[c][4 * g + i] * p.dropout_scale : 0.0f;
@@ -307,7 +307,7 @@ struct BwdParams {
   float* dgamma; float* dbeta;  // [d], accumulated with atomics (caller zero-fills)
   float* dbias;       // optional [d]: column sum of dz (or dx when dz is null)
   long long rows; int d; int S;
-  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed;
+  float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed; const unsigned long long* seed_src;
   long long dropout_ld;  // row pitch used for dropout element indices (N of the producing GEMM)
   const void* dres;      // optional residual-path gradient added to dx
 };
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kChunks <= 4 ? 3 : 1) ln_bwd_k
           const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.dropout_ld + col) >> 2;
 #pragma unroll
           for (int g = 0; g < V / 4; ++g) {
-            const uint64_t bits = dropout_bits4(p.dropout_seed, e4 + g);
+            const uint64_t bits = dropout_bits4(mix_seed(p.dropout_seed, p.seed_src), e4 + g);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               o[4 * g + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? o[4 * g + i] * p.dropout_scale : 0.0f;
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) ln_bwd_ring_kernel(const BwdP
           const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.dropout_ld + col) >> 2;
 #pragma unroll
           for (int q = 0; q < V / 4; ++q) {
-            const uint64_t bits = dropout_bits4(p.dropout_seed, e4 + q);
+            const uint64_t bits = dropout_bits4(mix_seed(p.dropout_seed, p.seed_src), e4 + q);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               o[4 * q + i] = dropout_keep_lane(bits, i, p.dropout_thr16) ? o[4 * q + i] * p.dropout_scale : 0.0f;
@@ -728,6 +728,7 @@ extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) 
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
     p.dropout_seed = a->dropout_seed;
+    p.seed_src = seed_source();
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // plain rows of up to 4 chunks (d <= 1024 bf16 / 512 fp32): bulk-copy ring kernel; embed mode and wider rows: register-prefetch kernel
@@ -767,6 +768,7 @@ extern "C" int tvt_layernorm_bwd(const tvt_layernorm_bwd_args* a, void* stream) 
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
     p.dropout_seed = a->dropout_seed;
+    p.seed_src = seed_source();
   }
   p.dropout_ld = a->d;
   p.dres = a->dres;

@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(256) split_kernel(const float* x, __nv_bfloat1
 // (short tensor-core accumulation chains, see ops.Mode.linear_fwd).
 template <typename T>
 __global__ void __launch_bounds__(256) bias_act_kernel(const float* x, const float* bias, T* y, const T* residual, T* preact, long long rows,
-                                                       long long cols, int act, float dscale, unsigned thr16, unsigned long long seed) {
+                                                       long long cols, int act, float dscale, unsigned thr16, unsigned long long seed,
+                                                       const unsigned long long* seed_src) {
+  seed = mix_seed(seed, seed_src);
   const long long n = rows * cols;
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
@@ -128,7 +130,8 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float* x, const flo
 // ---------------------------------------------------------------- positional encoding
 template <typename T>
 __global__ void __launch_bounds__(256) posenc_kernel(const T* x, const float* pe, T* y, long long rows, int d, int S, float dscale,
-                                                     unsigned thr16, unsigned long long seed) {
+                                                     unsigned thr16, unsigned long long seed, const unsigned long long* seed_src) {
+  seed = mix_seed(seed, seed_src);
   constexpr int V = Vec16<T>::kN;
   const long long n = rows * d;
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * V; i < n;
@@ -150,7 +153,8 @@ __global__ void __launch_bounds__(256) posenc_kernel(const T* x, const float* pe
 // ---------------------------------------------------------------- activation backward
 template <typename T>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const T* dy, const T* yz, T* dx, long long n, int act, float dscale, unsigned thr16,
-                                                      unsigned long long seed) {
+                                                      unsigned long long seed, const unsigned long long* seed_src) {
+  seed = mix_seed(seed, seed_src);
   constexpr int V = Vec16<T>::kN;
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * V; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x * V) {
@@ -171,8 +175,15 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* dy, const T* yz, 
 struct OptParams {
   float* p; const float* g; float* m; float* v; __nv_bfloat16* hi; __nv_bfloat16* lo; long long n; int kind; int first;
   float lr, b1, b2, eps, wd, mom, gs, bc1_inv, bc2_rsqrt;
+  const long long* step_dev;   // optional device-resident step count (whole-step CUDA graphs): overrides first / bc1_inv / bc2_rsqrt
 };
-__global__ void __launch_bounds__(256) optim_kernel(const OptParams a) {
+__global__ void __launch_bounds__(256) optim_kernel(OptParams a) {
+  if (a.step_dev != nullptr) {
+    const float t = static_cast<float>(__ldg(a.step_dev));
+    a.first = t <= 1.0f;
+    a.bc1_inv = 1.0f / (1.0f - powf(a.b1, t));
+    a.bc2_rsqrt = 1.0f / sqrtf(1.0f - powf(a.b2, t));
+  }
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < a.n; i += stride) {
     float p[4], g[4], m[4], v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -424,8 +435,8 @@ extern "C" int tvt_bias_act_fwd(const tvt_bias_act_args* a, void* stream) {
   if (a->dropout_p > 0.0f) { thr = (unsigned)(a->dropout_p * 65536.0f + 0.5f); sc = 65536.0f / (65536.0f - (float)thr); }
   const long long n4 = a->rows * a->cols / 4;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->out_dtype == TVT_F32) misc::bias_act_kernel<float><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (float*)a->y, (const float*)a->residual, (float*)a->preact, a->rows, a->cols, a->act, sc, thr, a->dropout_seed);
-  else misc::bias_act_kernel<__nv_bfloat16><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (__nv_bfloat16*)a->y, (const __nv_bfloat16*)a->residual, (__nv_bfloat16*)a->preact, a->rows, a->cols, a->act, sc, thr, a->dropout_seed);
+  if (a->out_dtype == TVT_F32) misc::bias_act_kernel<float><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (float*)a->y, (const float*)a->residual, (float*)a->preact, a->rows, a->cols, a->act, sc, thr, a->dropout_seed, seed_source());
+  else misc::bias_act_kernel<__nv_bfloat16><<<misc::grid1d(n4, 256), 256, 0, s>>>(a->x, a->bias, (__nv_bfloat16*)a->y, (const __nv_bfloat16*)a->residual, (__nv_bfloat16*)a->preact, a->rows, a->cols, a->act, sc, thr, a->dropout_seed, seed_source());
   return check_launch("tvt_bias_act_fwd");
 }
 
@@ -444,8 +455,8 @@ extern "C" int tvt_posenc_fwd(const tvt_posenc_args* a, void* stream) {
   if (a->dropout_p > 0.0f) { thr = (unsigned)(a->dropout_p * 65536.0f + 0.5f); sc = 65536.0f / (65536.0f - (float)thr); }
   const long long n = a->rows * a->d;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->dtype == TVT_F32) misc::posenc_kernel<float><<<misc::grid1d(n / 4, 256), 256, 0, s>>>((const float*)a->x, a->pe, (float*)a->y, a->rows, (int)a->d, (int)a->seq_len, sc, thr, a->dropout_seed);
-  else misc::posenc_kernel<__nv_bfloat16><<<misc::grid1d(n / 8, 256), 256, 0, s>>>((const __nv_bfloat16*)a->x, a->pe, (__nv_bfloat16*)a->y, a->rows, (int)a->d, (int)a->seq_len, sc, thr, a->dropout_seed);
+  if (a->dtype == TVT_F32) misc::posenc_kernel<float><<<misc::grid1d(n / 4, 256), 256, 0, s>>>((const float*)a->x, a->pe, (float*)a->y, a->rows, (int)a->d, (int)a->seq_len, sc, thr, a->dropout_seed, seed_source());
+  else misc::posenc_kernel<__nv_bfloat16><<<misc::grid1d(n / 8, 256), 256, 0, s>>>((const __nv_bfloat16*)a->x, a->pe, (__nv_bfloat16*)a->y, a->rows, (int)a->d, (int)a->seq_len, sc, thr, a->dropout_seed, seed_source());
   return check_launch("tvt_posenc_fwd");
 }
 
@@ -464,8 +475,8 @@ extern "C" int tvt_act_bwd(const tvt_act_bwd_args* a, void* stream) {
   if (a->dropout_p > 0.0f) { thr = (unsigned)(a->dropout_p * 65536.0f + 0.5f); sc = 65536.0f / (65536.0f - (float)thr); }
   const long long n = a->rows * a->cols;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->dtype == TVT_F32) misc::act_bwd_kernel<float><<<misc::grid1d(n / 4, 256), 256, 0, s>>>((const float*)a->dy, (const float*)a->y_or_z, (float*)a->dx, n, a->act, sc, thr, a->dropout_seed);
-  else misc::act_bwd_kernel<__nv_bfloat16><<<misc::grid1d(n / 8, 256), 256, 0, s>>>((const __nv_bfloat16*)a->dy, (const __nv_bfloat16*)a->y_or_z, (__nv_bfloat16*)a->dx, n, a->act, sc, thr, a->dropout_seed);
+  if (a->dtype == TVT_F32) misc::act_bwd_kernel<float><<<misc::grid1d(n / 4, 256), 256, 0, s>>>((const float*)a->dy, (const float*)a->y_or_z, (float*)a->dx, n, a->act, sc, thr, a->dropout_seed, seed_source());
+  else misc::act_bwd_kernel<__nv_bfloat16><<<misc::grid1d(n / 8, 256), 256, 0, s>>>((const __nv_bfloat16*)a->dy, (const __nv_bfloat16*)a->y_or_z, (__nv_bfloat16*)a->dx, n, a->act, sc, thr, a->dropout_seed, seed_source());
   return check_launch("tvt_act_bwd");
 }
 
@@ -474,7 +485,7 @@ extern "C" int tvt_optim_step(const tvt_optim_step_args* a, void* stream) {
   TVT_REQUIRE(a != nullptr && a->p && a->g && a->m, "tvt_optim_step: null pointer");
   TVT_REQUIRE(a->kind >= 0 && a->kind <= 2, "tvt_optim_step: kind must be 0 (AdamW), 1 (SGD) or 2 (Adagrad)");
   TVT_REQUIRE(a->kind == 1 || a->v, "tvt_optim_step: AdamW / Adagrad need the second-moment buffer");
-  TVT_REQUIRE(a->n >= 0 && a->step >= 1, "tvt_optim_step: bad n / step");
+  TVT_REQUIRE(a->n >= 0 && (a->step >= 1 || a->step_dev), "tvt_optim_step: bad n / step");
   TVT_REQUIRE(al16(a->p) && al16(a->g) && al16(a->m) && al16(a->v) && (reinterpret_cast<uintptr_t>(a->p_hi) & 7) == 0 &&
                   (reinterpret_cast<uintptr_t>(a->p_lo) & 7) == 0,
               "tvt_optim_step: buffers must be 16-byte aligned (bf16 planes 8-byte)");
@@ -487,8 +498,10 @@ extern "C" int tvt_optim_step(const tvt_optim_step_args* a, void* stream) {
   q.kind = a->kind; q.first = a->step == 1;
   q.lr = a->lr; q.b1 = a->beta1; q.b2 = a->beta2; q.eps = a->eps; q.wd = a->weight_decay; q.mom = a->momentum;
   q.gs = a->grad_scale == 0.0f ? 1.0f : a->grad_scale;
-  q.bc1_inv = 1.0f / (1.0f - powf(a->beta1, (float)a->step));
-  q.bc2_rsqrt = 1.0f / sqrtf(1.0f - powf(a->beta2, (float)a->step));
+  const float t = (float)(a->step >= 1 ? a->step : 1);
+  q.bc1_inv = 1.0f / (1.0f - powf(a->beta1, t));
+  q.bc2_rsqrt = 1.0f / sqrtf(1.0f - powf(a->beta2, t));
+  q.step_dev = reinterpret_cast<const long long*>(a->step_dev);
   misc::optim_kernel<<<misc::grid1d((a->n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
   return check_launch("tvt_optim_step");
 }
@@ -622,7 +635,8 @@ __device__ __forceinline__ float aug_u01(uint32_t w) { return (static_cast<float
 
 template <typename T>
 __global__ void __launch_bounds__(256) feature_augment_kernel(const float* x, T* y, long long rows, int d_in, int d_out, float p_drop,
-                                                              float p_noise, float noise_std, unsigned long long seed) {
+                                                              float p_noise, float noise_std, unsigned long long seed, const unsigned long long* seed_src) {
+  seed = mix_seed(seed, seed_src);
   uint32_t rk[kDropoutRounds], rkn[kDropoutRounds];
 #pragma unroll
   for (int r = 0; r < kDropoutRounds; ++r) rk[r] = rkn[r] = static_cast<uint32_t>(seed) + r * kDropoutWeyl;
@@ -679,8 +693,8 @@ extern "C" int tvt_feature_augment(const tvt_feature_augment_args* a, void* stre
   const long long items = a->rows * (a->d_out / 4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->out_dtype == TVT_F32)
-    misc::feature_augment_kernel<float><<<misc::grid1d(items, 256), 256, 0, s>>>(a->x, (float*)a->y, a->rows, (int)a->d_in, (int)a->d_out, a->p_drop, a->p_noise, a->noise_std, a->seed);
+    misc::feature_augment_kernel<float><<<misc::grid1d(items, 256), 256, 0, s>>>(a->x, (float*)a->y, a->rows, (int)a->d_in, (int)a->d_out, a->p_drop, a->p_noise, a->noise_std, a->seed, seed_source());
   else
-    misc::feature_augment_kernel<__nv_bfloat16><<<misc::grid1d(items, 256), 256, 0, s>>>(a->x, (__nv_bfloat16*)a->y, a->rows, (int)a->d_in, (int)a->d_out, a->p_drop, a->p_noise, a->noise_std, a->seed);
+    misc::feature_augment_kernel<__nv_bfloat16><<<misc::grid1d(items, 256), 256, 0, s>>>(a->x, (__nv_bfloat16*)a->y, a->rows, (int)a->d_in, (int)a->d_out, a->p_drop, a->p_noise, a->noise_std, a->seed, seed_source());
   return check_launch("tvt_feature_augment");
 }

@@ -16,6 +16,8 @@ int num_sms();
 int check_launch(const char* what);
 // TVT_EARCH unless the current device is compute capability 10.x.
 int require_sm100();
+// Device pointer registered with tvt_set_seed_source (nullptr when none): see mix_seed below.
+const unsigned long long* seed_source();
 
 #define TVT_REQUIRE(cond, ...)          \
   do {                                  \
@@ -173,6 +175,16 @@ __device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t elem_d
   dropout_words(rk, static_cast<uint32_t>(elem_div4), static_cast<uint32_t>(elem_div4 >> 32) ^ static_cast<uint32_t>(seed >> 32), lo, hi);
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
+// Whole-step CUDA graphs bake every kernel argument, the dropout seeds included, so the step-to-step variation of the masks
+// comes from DEVICE memory: when the library has a seed source (tvt_set_seed_source: a device-resident step counter that a
+// one-thread kernel at the head of the captured step advances) its hash is folded into the high word of every seed.  Only the
+// high word changes, so the round keys that some kernels hoist to launch constants (low word) stay valid.
+__device__ __forceinline__ unsigned long long mix_seed(unsigned long long seed, const unsigned long long* src) {
+  if (src == nullptr) return seed;
+  const unsigned long long h = __ldg(src) * 0x9E3779B97F4A7C15ull;
+  return seed ^ (h & 0xFFFFFFFF00000000ull);
+}
+
 // Lane i (0..3) survives dropout when its 16 random bits are >= thr16 (= p * 65536).
 __device__ __forceinline__ bool dropout_keep_lane(uint64_t bits, int i, uint32_t thr16) {
   return (static_cast<uint32_t>(bits >> (16 * i)) & 0xFFFFu) >= thr16;

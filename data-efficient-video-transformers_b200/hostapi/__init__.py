@@ -6,7 +6,7 @@ from .frame_transformer import TransformerBase, FrameStream, FrameTransformer, I
 from .TPN import (Reasoning, sum_group, SpatialPyramid, Feature_Pyramid_low, Feature_Pyramid_Mid,  # noqa: F401
                   Feature_Pyramid_High, TPN, ResNetMaps)
 from .fusion import CrossModalBlock, ExpertStream, FusionTransformer, DistillationTrainer  # noqa: F401
-from .inference import EvalBuffer, GraphedForward, REFERENCE_THRESHOLDS  # noqa: F401
+from .inference import EvalBuffer, GraphedForward, GraphedTrainStep, REFERENCE_THRESHOLDS  # noqa: F401
 from .collabgating import CollaborativeGating  # noqa: F401
 from .loader import FeatureAugment  # noqa: F401
 from . import vit  # noqa: F401,E402

@@ -160,3 +160,93 @@ class GraphedForward:
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class GraphedTrainStep:
+    """Whole-step CUDA graph of a TRAINING step: ``step_fn(*inputs) -> loss`` (zero_grad, forward, backward, bucket
+    all-reduces, optimizer step — everything the step launches) is captured once per distinct set of input buffers and
+    replayed with a single launch.  The launch-bound BASELINE configs (C1: ~100 kernels of a few microseconds each) spend
+    most of a step in launch gaps; a replay has none.
+
+    What changes from step to step cannot be a kernel argument inside a graph, so it lives in device memory:
+      * dropout masks: ``tvt_set_seed_source`` registers a device step counter; every mask-drawing kernel folds its hash
+        into the (baked) seed, forward and backward alike; the first node of the graph advances the counter;
+      * the optimizer's bias-correction step count: ``FlatOptimizer.step_dev`` (the element next to the seed counter).
+    The gradient buckets, optimizer state and bf16 weight planes are persistent buffers updated in place, so their
+    addresses are stable by construction (``optim.FlatOptimizer`` is required: a torch optimizer would re-split weights).
+    Replaying with inputs at new addresses captures another graph that shares the first one's memory pool; the returned loss
+    is a static tensor overwritten by the next replay.  Eager calls of ``step_fn`` stay valid between replays (they fold the
+    same device counter)."""
+
+    def __init__(self, step_fn, optimizer, example_inputs=None, warmup=3):
+        from .. import capi
+        self.step_fn, self.opt = step_fn, optimizer
+        dev = optimizer.buckets[0]["p"].device
+        self.counters = torch.zeros(2, dtype=torch.int64, device=dev)          # [dropout step counter, optimizer step count]
+        self.counters[1] = optimizer.step_count
+        optimizer.step_dev = self.counters[1:]
+        capi.set_seed_source(self.counters.data_ptr())
+        self.graphs = {}
+        self.pool = None
+        self.warmup = warmup
+        self.kernels_per_replay = 0
+        self._warm = False
+        if example_inputs is not None:
+            self._graph_for(example_inputs)
+
+    @staticmethod
+    def _flat(inputs):
+        out = []
+        for x in inputs:
+            out.extend(x) if isinstance(x, (list, tuple)) else out.append(x)
+        return out
+
+    def _advance(self):
+        from .. import capi
+        capi.step_counter_advance(self.counters.data_ptr(), 2, torch.cuda.current_stream().cuda_stream)
+
+    def _graph_for(self, inputs):
+        from .. import capi
+        key = tuple(t.data_ptr() for t in self._flat(inputs))
+        ent = self.graphs.get(key)
+        if ent is not None:
+            return ent
+        if not self._warm:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):       # lazy initialisation (kernel attributes, weight planes, autograd, NCCL) outside the graph
+                    self._advance()
+                    self.step_fn(*inputs)
+            torch.cuda.current_stream().wait_stream(side)
+            self._warm = True
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = capi.launches
+        from .. import functions
+        self.capture_seed_counter = functions._seed_counter[0]     # the baked host seeds derive from this (tests replay it eagerly)
+        with torch.cuda.graph(g, pool=self.pool):
+            self._advance()
+            loss = self.step_fn(*inputs)
+        self.kernels_per_replay = capi.launches - l0
+        if self.pool is None:
+            self.pool = g.pool()
+        ent = (g, loss, inputs)                    # the inputs are kept alive: the graph reads their addresses
+        self.graphs[key] = ent
+        return ent
+
+    def prepare(self, *inputs):
+        """Capture the graph for this set of input buffers now (e.g. before a timed region)."""
+        self._graph_for(inputs)
+
+    def __call__(self, *inputs):
+        g, loss, _ = self._graph_for(inputs)
+        g.replay()
+        self.opt.step_count += 1
+        return loss
+
+    def close(self):
+        from .. import capi
+        capi.set_seed_source(None)
+        self.opt.step_dev = None
+        self.graphs.clear()

@@ -21,6 +21,7 @@ class FlatOptimizer:
         self.kind = {"adamw": 0, "sgd": 1, "adagrad": 2}[kind]
         self.lr, self.betas, self.eps, self.weight_decay, self.momentum = lr, betas, eps, weight_decay, momentum
         self.step_count = 0
+        self.step_dev = None        # device int64 step count (set by hostapi.GraphedTrainStep): the kernel reads it instead of step_count
         self.buckets = []
         want_lo = any(m.fp32 for m in self.modes)
         for b in reducer.buckets:
@@ -53,6 +54,7 @@ class FlatOptimizer:
             a.p_hi = b["hi"].data_ptr() if b["hi"] is not None else None
             a.p_lo = b["lo"].data_ptr() if b["lo"] is not None else None
             a.n, a.kind, a.step = b["p"].numel(), self.kind, self.step_count
+            a.step_dev = self.step_dev.data_ptr() if self.step_dev is not None else None
             a.lr, a.beta1, a.beta2, a.eps = self.lr, self.betas[0], self.betas[1], self.eps
             a.weight_decay, a.momentum, a.grad_scale = self.weight_decay, self.momentum, scale
             capi.call("tvt_optim_step", a, stream)

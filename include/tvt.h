@@ -45,6 +45,17 @@ TVT_API int tvt_version(void);
 /* TVT_OK when the current CUDA device is a B200-class part (compute capability 10.x). */
 TVT_API int tvt_device_check(void);
 
+/* Whole-step CUDA graphs (the training step of the launch-bound BASELINE configs replayed with one launch): a captured
+ * graph bakes every kernel argument, so what must change from step to step lives in DEVICE memory instead.
+ *   tvt_set_seed_source(ptr)        registers a device uint64 step counter (NULL = none; the default).  While one is registered,
+ *                                   every kernel that draws a dropout mask folds a hash of *ptr into its seed's high word,
+ *                                   forward and backward alike (the backward recomputes the forward's mask).
+ *   tvt_step_counter_advance(p,n,s) one-thread kernel: p[0..n) += 1 (the seed counter and, next to it, the optimizer's step
+ *                                   count read through tvt_optim_step_args.step_dev); the first node of a captured step.
+ * Process-wide setting, not thread-safe against concurrent launches (the reference drives its model from one Python thread). */
+TVT_API int tvt_set_seed_source(const void* device_counter);
+TVT_API int tvt_step_counter_advance(void* device_counters, int count, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators, fused epilogue).
  * Replaces every aten::addmm / aten::mm the reference reaches through
@@ -399,6 +410,7 @@ typedef struct {
   int32_t kind;
   int32_t step; /* 1-based */
   float lr, beta1, beta2, eps, weight_decay, momentum, grad_scale;
+  const void* step_dev; /* optional device int64: the 1-based step count read by the kernel (overrides `step`), for whole-step CUDA graphs */
 } tvt_optim_step_args;
 TVT_API int tvt_optim_step(const tvt_optim_step_args* args, void* stream);
 

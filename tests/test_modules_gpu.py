@@ -614,3 +614,62 @@ def test_direct_gradient_sinks_match_autograd_accumulation(api, precision):
     for n in grads[False]:
         assert_close(grads[True][n], grads[False][n], 1e-5 if precision == "fp32" else 1e-6, "direct " + n)
     assert ddp.direct_target(next(mod.parameters())) is None   # removed reducers no longer capture gradients
+
+
+@pytest.mark.parametrize("pyramid", [False, True])
+def test_graphed_training_step_matches_eager_steps(api, pyramid):
+    """Whole-step CUDA graph (zero_grad + teacher forward + student forward / backward + flat-bucket AdamW) replayed twice
+    == the same two steps launched eagerly from the same state: dropout p = 0.5 everywhere, so this also proves that the
+    masks of a replay come from the DEVICE step counter (a graph that replayed baked seeds would repeat step 1's masks in
+    step 2) and that forward and backward of a replay regenerate the same masks.  Parameters / losses agree to fp32
+    round-off of the split-K atomics, not bit for bit."""
+    from tvt_b200 import ddp, optim, functions
+    B = 16
+    common = dict(d=128, nhead=2, nhid=256, nlayers=2, dropout=0.5, batch_size=B, frames=16, n_classes=15, precision="bf16")
+    torch.manual_seed(1130)
+    teacher = api.FusionTransformer(in_dims=(256, 64), fusion="cross", **common).to(DEV)
+    student = api.FusionTransformer(in_dims=(256,), fusion="sum", pyramid=pyramid, **common).to(DEV)
+    trainer = api.DistillationTrainer(teacher, student, temperature=2.0, alpha=1.0).train()
+    red = ddp.GradBucketReducer([p for p in student.parameters()], bucket_bytes=1 << 18, average=False)
+    opt = optim.FlatOptimizer(red, modes=[student.mode], kind="adamw", lr=1e-3, weight_decay=0.01)
+    gen = torch.Generator().manual_seed(3)
+    batches = [([torch.randn(B, 16, D, generator=gen).to(DEV).bfloat16() for D in (256, 64)], _targets(B, 15, gen).to(DEV)) for _ in range(2)]
+
+    def step(xs, y):
+        red.zero_grad()
+        loss = trainer.training_step({"experts": xs, "label": y})
+        loss.backward()
+        red.finish()
+        opt.step()
+        return loss
+
+    stepper = api.GraphedTrainStep(step, opt, batches[0])
+    stepper.prepare(*batches[1])
+    seed0 = stepper.capture_seed_counter
+    state = [(b["p"].clone(), b["m"].clone(), b["v"].clone()) for b in opt.buckets]
+    ctr0 = stepper.counters.clone()
+    graph_losses = [float(stepper(*batches[i])) for i in range(2)]
+    graph_params = [b["p"].clone() for b in opt.buckets]
+    assert stepper.kernels_per_replay > 50 and len(stepper.graphs) == 2
+    assert int(stepper.counters[0]) == int(ctr0[0]) + 2
+    # restore the state and run the same two steps eagerly (same baked host seeds, same device counter values)
+    for b, (p_, m_, v_) in zip(opt.buckets, state):
+        b["p"].copy_(p_); b["m"].copy_(m_); b["v"].copy_(v_)
+        if b["hi"] is not None:
+            b["hi"].copy_(p_.bfloat16())
+    stepper.counters.copy_(ctr0)
+    eager_losses = []
+    for i in range(2):
+        functions._seed_counter[0] = seed0
+        stepper._advance()
+        eager_losses.append(float(step(*batches[i])))
+    for a, b in zip(graph_losses, eager_losses):
+        assert abs(a - b) <= 1e-4 * abs(b), (graph_losses, eager_losses)
+    assert abs(graph_losses[0] - graph_losses[1]) > 1e-3 * abs(graph_losses[0])          # different batches / masks
+    for gp, b in zip(graph_params, opt.buckets):
+        assert_close(gp, b["p"], 1e-5, "parameters after two replays vs two eager steps")
+    # a replay on the SAME batch draws new masks each time (the device counter advanced)
+    l1, l2 = float(stepper(*batches[0])), float(stepper(*batches[0]))
+    assert l1 != l2
+    stepper.close()
+    red.remove()

@@ -150,7 +150,11 @@ def summarize():
         ex = [r for r in grads if r["exempt"]]
         parts = [f"parity[{case}]:"]
         if other:
-            parts.append(", ".join(f"{r['what']} {r['err']:.2e}" for r in other))
+            shown = ", ".join(f"{r['what']} {r['err']:.2e}" for r in other[:6])
+            if len(other) > 6:
+                w = max(other, key=lambda r: r["err"])
+                shown += f", ... {len(other)} checks, worst {w['err']:.2e} ({w['what']})"
+            parts.append(shown)
         if grads:
             w = max(grads, key=lambda r: r["err"])
             parts.append(f"{len(grads)} param grads, worst {w['err']:.2e} ({w['what'][5:]}), tol {w['tol']:.0e}, "

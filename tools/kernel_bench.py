@@ -80,6 +80,21 @@ for D, Dout in ((2048, 2048), (1024, 1024), (128, 2048)):
     report(f"feature_augment [{B * 128},{D}]->{Dout} f32->bf16", ms, bytes_=B * 128 * (D * 4.0 + Dout * 2.0))
 del xr
 
+# ---- spatial pyramid pooling (TPN.py:2-40): C3's 128 clips x 64 frames = 8192 frames of (128,28,28) + (256,14,14) + (512,7,7)
+frames = 8192 if "--small" not in sys.argv else 2048
+for Cc, s_ in ((128, 28), (256, 14), (512, 7)):
+    for dt in (torch.bfloat16, torch.float32):
+        maps = [torch.randn(frames, Cc, s_, s_, device=dev, generator=g).to(dt) for _ in range(2)]
+        pooled = torch.empty(frames, Cc, device=dev)
+        ms = timeit(lambda i: ops.spatial_pool(maps[i % 2], pooled, 0))
+        nm = "bf16" if dt == torch.bfloat16 else "f32"
+        report(f"spatial_pool_fwd [{frames},{Cc},{s_},{s_}] {nm}", ms, bytes_=frames * Cc * (s_ * s_ * maps[0].element_size() + 4.0))
+        ms = timeit(lambda i: ops.spatial_pool_bwd(pooled, maps[i % 2], 0))
+        report(f"spatial_pool_bwd [{frames},{Cc},{s_},{s_}] {nm}", ms, bytes_=frames * Cc * (s_ * s_ * maps[0].element_size() + 4.0))
+        del maps
+if "--only-bandwidth" in sys.argv:
+    sys.exit(0)
+
 # ---- GEMMs of one encoder layer (forward, dgrad, wgrad)
 mode = ops.Mode("bf16")
 def gemm_case(name, M, N, K, **kw):
