@@ -231,16 +231,17 @@ class GraphedTrainStep:
         self.kernels_per_replay = capi.launches - l0
         if self.pool is None:
             self.pool = g.pool()
-        ent = (g, loss, inputs)                    # the inputs are kept alive: the graph reads their addresses
+        ent = (g, loss, inputs, self.capture_seed_counter)   # the inputs are kept alive: the graph reads their addresses
         self.graphs[key] = ent
         return ent
 
     def prepare(self, *inputs):
-        """Capture the graph for this set of input buffers now (e.g. before a timed region)."""
-        self._graph_for(inputs)
+        """Capture the graph for this set of input buffers now (e.g. before a timed region).  Returns the value the host
+        seed counter (functions._seed_counter) had when the graph's seeds were drawn."""
+        return self._graph_for(inputs)[3]
 
     def __call__(self, *inputs):
-        g, loss, _ = self._graph_for(inputs)
+        g, loss = self._graph_for(inputs)[:2]
         g.replay()
         self.opt.step_count += 1
         return loss

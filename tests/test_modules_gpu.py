@@ -644,8 +644,7 @@ def test_graphed_training_step_matches_eager_steps(api, pyramid):
         return loss
 
     stepper = api.GraphedTrainStep(step, opt, batches[0])
-    stepper.prepare(*batches[1])
-    seed0 = stepper.capture_seed_counter
+    seeds = [stepper.prepare(*batches[0]), stepper.prepare(*batches[1])]     # host seed counter baked into each graph
     state = [(b["p"].clone(), b["m"].clone(), b["v"].clone()) for b in opt.buckets]
     ctr0 = stepper.counters.clone()
     graph_losses = [float(stepper(*batches[i])) for i in range(2)]
@@ -660,7 +659,7 @@ def test_graphed_training_step_matches_eager_steps(api, pyramid):
     stepper.counters.copy_(ctr0)
     eager_losses = []
     for i in range(2):
-        functions._seed_counter[0] = seed0
+        functions._seed_counter[0] = seeds[i]
         stepper._advance()
         eager_losses.append(float(step(*batches[i])))
     for a, b in zip(graph_losses, eager_losses):
