@@ -44,7 +44,7 @@ WORKLOADS = {
 }
 N_CLASSES = 15
 # whole-step CUDA-graph replay for the launch-bound configs (C1-C4) unless --graph says otherwise
-GRAPH_SMALL_CONFIGS = False
+GRAPH_SMALL_CONFIGS = True
 
 
 def flops_per_clip(w):
