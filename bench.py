@@ -43,8 +43,8 @@ WORKLOADS = {
                teacher=(2048, 1024, 128), student_dims=(2048,), pyramid=True, distill=True),
 }
 N_CLASSES = 15
-# whole-step CUDA-graph replay for the launch-bound configs (C1-C4) unless --graph says otherwise
-GRAPH_SMALL_CONFIGS = True
+# whole-step CUDA-graph replay of the training step (hostapi.GraphedTrainStep) unless --graph 0: 4x at C1, 2.5x at C2, ~1 % at C5
+GRAPH_DEFAULT = True
 
 
 def flops_per_clip(w):
@@ -320,12 +320,19 @@ def run_tvt(w, args, ctx, steps, warmup, sample_clocks=False, graph=None):
         return ms / nsteps
 
     stepper = None
+    step_fn = lambda xs, y: gpu_step(w, model, reducer, opt, xs, y)   # noqa: E731
     if graph:
         from tvt_b200.hostapi import GraphedTrainStep
-        stepper = GraphedTrainStep(lambda xs, y: gpu_step(w, model, reducer, opt, xs, y), opt, resident[0], warmup=3)
-        step_fn = lambda xs, y: stepper(xs, y)            # noqa: E731
-    else:
-        step_fn = lambda xs, y: gpu_step(w, model, reducer, opt, xs, y)   # noqa: E731
+        try:
+            stepper = GraphedTrainStep(lambda xs, y: gpu_step(w, model, reducer, opt, xs, y), opt, resident[0], warmup=3)
+            stepper.prepare(*resident[1])
+            step_fn = lambda xs, y: stepper(xs, y)            # noqa: E731
+        except Exception as e:      # every rank runs the same deterministic program, so all ranks fall back together
+            print(f"bench.py: CUDA-graph capture of the training step failed ({e!r:.200}); falling back to eager launches", file=sys.stderr)
+            if stepper is not None:
+                stepper.close()
+            stepper, graph = None, False
+            torch.cuda.synchronize()
 
     # ---- leg 1: inputs resident in HBM
     for i in range(warmup):
@@ -347,7 +354,7 @@ def run_tvt(w, args, ctx, steps, warmup, sample_clocks=False, graph=None):
     slots = [([torch.empty_like(x, device=dev) for x in xs], torch.empty_like(y, device=dev)) for xs, y in host]
     slot_free = [None, None]
     if stepper is not None:
-        for sl in slots + resident:
+        for sl in slots:
             stepper.prepare(*sl)                            # one graph per input buffer set, captured outside the timed regions
 
     def prefetch(i):
@@ -469,8 +476,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="strong: the workload's batch is the GLOBAL batch, split evenly over the ranks (SURVEY 8e: C4 256 -> 128/64/32)")
     ap.add_argument("--host-dtype", default="bf16", choices=["bf16", "fp32"], help="dtype of the pinned host feature batches (e2e leg)")
-    ap.add_argument("--graph", type=int, default=-1, help="1: replay the whole training step as a CUDA graph; 0: eager launches; "
-                                                          "-1 (default): graph for the launch-bound configs c1-c4, eager for c5")
+    ap.add_argument("--graph", type=int, default=-1, help="1 (default): replay the whole training step as a CUDA graph; 0: eager launches")
     ap.add_argument("--cpu-clips", type=int, default=0, help="clips per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the C1-C4 lines and the stock-PyTorch-on-GPU yardstick")
@@ -518,7 +524,7 @@ def main():
         global_batch = w["batch"]
         w["batch"] //= world
     B = w["batch"]
-    use_graph = (GRAPH_SMALL_CONFIGS and args.workload != "c5") if args.graph < 0 else bool(args.graph)
+    use_graph = GRAPH_DEFAULT if args.graph < 0 else bool(args.graph)
     args.graph = use_graph
     r = run_tvt(w, args, ctx, args.steps, args.warmup, sample_clocks=True)
 
@@ -532,7 +538,7 @@ def main():
                 if scaling == "strong":
                     gb = wx["batch"]
                     wx["batch"] //= world
-                rx = run_tvt(wx, args, ctx, min(args.steps, 20), 3, graph=(args.graph if args.graph_explicit else GRAPH_SMALL_CONFIGS))
+                rx = run_tvt(wx, args, ctx, min(args.steps, 20), 3, graph=(args.graph if args.graph_explicit else GRAPH_DEFAULT))
                 extras[name if scaling == "weak" else name + "_strong"] = (wx, gb, scaling, rx)
 
     if rank != 0:
