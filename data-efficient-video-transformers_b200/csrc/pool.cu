@@ -178,9 +178,13 @@ __global__ void __launch_bounds__(kSpatialThreads) spatial_tile_kernel(const Spa
     const T* t = reinterpret_cast<const T*>(sp_smem + slot * kSpatialTileBytes);
     const long long r0 = tile * R;
     const int nr = static_cast<int>(rows - r0 < R ? rows - r0 : R);
+    const long long f0 = r0 / p.C;                      // one 64-bit division per tile; rows step from it
+    const int c_first = static_cast<int>(r0 - f0 * p.C), Cc = static_cast<int>(p.C);
     auto emit = [&](int r, float acc) {
-      const long long fc = r0 + r, f = fc / p.C, c = fc - f * p.C;
-      const long long o = f * p.ld_out + p.col_off + c;
+      int c = c_first + r;
+      const int df = c / Cc;                              // 32-bit
+      c -= df * Cc;
+      const long long o = (f0 + df) * p.ld_out + p.col_off + c;
       if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = acc * inv;
       else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(acc * inv);
     };
@@ -193,13 +197,56 @@ __global__ void __launch_bounds__(kSpatialThreads) spatial_tile_kernel(const Spa
         if (i < hw) a0 += Elem<T>::to_f(row[i]);
         emit(r, a0 + a1);
       }
+    } else if (hw < 512) {
+      // medium rows (14 x 14 = 196): EIGHT lanes per row, four rows per warp pass - a warp per row would spend more
+      // instructions on the shuffle tree and the output address than on the row's few loads.  Each lane sums a contiguous
+      // eighth of the row (chunk starts 25 words apart: spread over the banks)
+      const int sub = lane >> 3, l8 = lane & 7;
+      const bool words = sizeof(T) == 2 && (hw & 1) == 0;   // bf16 rows of even length start 4-byte aligned: two elements per load
+      const int n = words ? hw >> 1 : hw, seg = (n + 7) >> 3;
+      for (int base = warp * 4; base < nr; base += (kSpatialThreads / 32) * 4) {
+        const int r = base + sub;
+        const bool valid = r < nr;
+        float a0 = 0.0f, a1 = 0.0f;
+        if (valid) {
+          const int i0 = l8 * seg, i1 = i0 + seg < n ? i0 + seg : n;
+          if (words) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(t + r * hw);
+            for (int i = i0; i < i1; ++i) {
+              const uint32_t w = rw[i];
+              a0 += __uint_as_float(w << 16);
+              a1 += __uint_as_float(w & 0xFFFF0000u);
+            }
+          } else {
+            const T* row = t + r * hw;
+            int i = i0;
+            for (; i + 1 < i1; i += 2) { a0 += Elem<T>::to_f(row[i]); a1 += Elem<T>::to_f(row[i + 1]); }
+            if (i < i1) a0 += Elem<T>::to_f(row[i]);
+          }
+        }
+        float acc = a0 + a1;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (valid && l8 == 0) emit(r, acc);
+      }
     } else {
       for (int r = warp; r < nr; r += kSpatialThreads / 32) {
         const T* row = t + r * hw;
         float a0 = 0.0f, a1 = 0.0f;
-        int i = lane;
-        for (; i + 32 < hw; i += 64) { a0 += Elem<T>::to_f(row[i]); a1 += Elem<T>::to_f(row[i + 32]); }
-        if (i < hw) a0 += Elem<T>::to_f(row[i]);
+        if (sizeof(T) == 2 && (hw & 1) == 0) {            // bf16 rows of even length start 4-byte aligned: two elements per load
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(row);
+          const int nw = hw >> 1;
+          for (int i = lane; i < nw; i += 32) {
+            const uint32_t w = rw[i];
+            a0 += __uint_as_float(w << 16);
+            a1 += __uint_as_float(w & 0xFFFF0000u);
+          }
+        } else {
+          int i = lane;
+          for (; i + 32 < hw; i += 64) { a0 += Elem<T>::to_f(row[i]); a1 += Elem<T>::to_f(row[i + 32]); }
+          if (i < hw) a0 += Elem<T>::to_f(row[i]);
+        }
         const float acc = warp_sum(a0 + a1);
         if (lane == 0) emit(r, acc);
       }
@@ -340,7 +387,8 @@ extern "C" int tvt_spatial_pool_fwd(const tvt_spatial_pool_args* a, void* stream
   long long R = (pool::kSpatialTileBytes / (r0 * row_bytes)) * r0;
   // the final (partial) tile must also be a whole number of 16-byte units: true when rows % r0 == 0
   if (R > 0 && al16(a->x) && rows % r0 == 0 && a->hw < (1 << 20)) {
-    if (R >= 16) R -= R % 8;                                     // whole rounds of the 8 warps
+    if (R >= 64) R -= R % 32;                                    // whole passes of the 8 warps (4 rows each for medium rows)
+    else if (R >= 16) R -= R % 8;
     p.rows_per_tile = R;
     p.ntiles = (rows + R - 1) / R;
     static bool attr_set = false;
