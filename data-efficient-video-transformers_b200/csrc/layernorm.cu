@@ -21,6 +21,9 @@ struct FwdParams {
   long long rows; int d; int S;  // S > 0 selects embed mode (rows = B * S)
   float eps;
   float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed; const unsigned long long* seed_src;
+  int reverse;        // ring kernels: walk the rows from the LAST pair to the first.  The producer (a GEMM epilogue) has just
+                      // written these rows in ascending order through an L2 smaller than its traffic, so the rows written last
+                      // are the ones still resident: reading them first turns DRAM reads into L2 hits
 };
 
 template <typename T, int kChunks>
@@ -177,7 +180,8 @@ __global__ void __launch_bounds__(kRingWarps * 32) ln_fwd_ring_kernel(const FwdP
   const uint32_t row_bytes = static_cast<uint32_t>(p.d) * sizeof(T);
   const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring_raw)) + warp * kRing * 2 * row_bytes;
   const uint32_t bar_s = static_cast<uint32_t>(__cvta_generic_to_shared(&bars[warp][0]));
-  auto fetch = [&](long long q, int slot) {      // rows 2q, 2q + 1 (the last pair may be a single row)
+  auto fetch = [&](long long qi, int slot) {     // rows 2q, 2q + 1 (the last pair may be a single row)
+    const long long q = p.reverse ? npairs - 1 - qi : qi;
     const uint32_t bytes = 2 * q + 1 < p.rows ? 2 * row_bytes : row_bytes;
     bulk_load_rows(ring_s + slot * 2 * row_bytes, reinterpret_cast<const T*>(p.x) + 2 * q * p.d, bytes, bar_s + 8 * slot);
   };
@@ -201,7 +205,8 @@ __global__ void __launch_bounds__(kRingWarps * 32) ln_fwd_ring_kernel(const FwdP
   const float inv_d = 1.0f / p.d;
   int slot = 0;
   uint32_t parity = 0;
-  for (long long q = pair0; q < npairs; q += stride) {
+  for (long long qi = pair0; qi < npairs; qi += stride) {
+    const long long q = p.reverse ? npairs - 1 - qi : qi;     // see FwdParams::reverse
     bar_wait(bar_s + 8 * slot, parity);
     float v[2][kChunks][V];
 #pragma unroll
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) ln_fwd_ring_kernel(const FwdP
       s1[1] += __shfl_xor_sync(0xffffffffu, s1[1], o);
     }
     // every lane's slot data went into the shuffle tree above, so the slot can be refilled: kRing pairs ahead
-    if (lane == 0 && q + kRing * stride < npairs) fetch(q + kRing * stride, slot);
+    if (lane == 0 && qi + kRing * stride < npairs) fetch(qi + kRing * stride, slot);
     const float mean[2] = {s1[0] * inv_d, s1[1] * inv_d};
     float s2[2] = {0.0f, 0.0f};
 #pragma unroll
@@ -722,6 +727,8 @@ extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) 
   int rc = require_sm100();
   if (rc != TVT_OK) return rc;
   ln::FwdParams p{};
+  static const int ln_reverse = [] { const char* e = getenv("TVT_LN_REVERSE"); return e ? atoi(e) : 1; }();
+  p.reverse = ln_reverse;
   p.x = a->x; p.cls = a->cls; p.pe = a->pe; p.gamma = a->gamma; p.beta = a->beta; p.y = a->y; p.pre = a->pre;
   p.mean = a->mean; p.rstd = a->rstd; p.rows = a->rows; p.d = (int)a->d; p.S = (int)a->seq_len; p.eps = a->eps;
   if (a->dropout_p > 0.0f) {
