@@ -155,7 +155,7 @@ def test_shared_parameters_complete_only_after_their_last_contribution(api, prec
         grads[direct] = {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None}
         red.remove()
     for n in grads[False]:
-        assert_close(grads[True][n], grads[False][n], 2e-6 if precision == "fp32" else 1e-5, "shared direct " + n)
+        assert_close(grads[True][n], grads[False][n], 1e-5, "shared direct " + n)      # fp32 atomics: summation order varies
 
 
 def test_graphed_forward_recaptures_after_a_weight_update(api):
