@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libtvt_b200.so")
-SOURCES = ["core.cu", "gemm_sm100.cu", "layernorm.cu", "attention_simt.cu", "attention_sm100.cu", "pool.cu", "loss.cu", "misc.cu"]
+SOURCES = ["core.cu", "gemm_sm100.cu", "layernorm.cu", "attention_simt.cu", "attention_sm100.cu", "pool.cu", "loss.cu", "misc.cu", "collab.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -79,6 +79,19 @@ class SpatialPoolBwdArgs(C.Structure):
                 ("col_offset", i64), ("dtype", i32), ("reserved", i32)]
 
 
+class StretchCastArgs(C.Structure):
+    _fields_ = [("x", vp), ("y", vp), ("rows", i64), ("d_in", i64), ("d_out", i64), ("ld_out", i64), ("out_dtype", i32), ("reserved", i32)]
+
+
+class CollabArgs(C.Structure):
+    _fields_ = [("c", vp), ("pc", vp), ("a", vp), ("out", vp), ("dout", vp), ("dc", vp), ("dpc", vp), ("da", vp), ("rows", i64), ("d", i64),
+                ("experts", i32), ("dtype", i32)]
+
+
+class L2NormArgs(C.Structure):
+    _fields_ = [("x", vp), ("y", vp), ("inv_norm", vp), ("dy", vp), ("dx", vp), ("rows", i64), ("d", i64), ("eps", f32), ("dtype", i32)]
+
+
 class DistillLossArgs(C.Structure):
     _fields_ = [("student", vp), ("teacher", vp), ("target", vp), ("losses", vp), ("dlogits", vp), ("batch", i64),
                 ("classes", i64), ("w_bce", f32), ("w_ce", f32), ("w_kl", f32), ("temperature", f32), ("grad_scale", f32)]
@@ -159,6 +172,13 @@ ENTRY_POINTS = {
     "tvt_spatial_pool_fwd": SpatialPoolArgs,
     "tvt_spatial_pool_bwd": SpatialPoolBwdArgs,
     "tvt_distill_loss": DistillLossArgs,
+    "tvt_stretch_cast": StretchCastArgs,
+    "tvt_collab_mix_fwd": CollabArgs,
+    "tvt_collab_mix_bwd": CollabArgs,
+    "tvt_collab_gate_fwd": CollabArgs,
+    "tvt_collab_gate_bwd": CollabArgs,
+    "tvt_l2norm_fwd": L2NormArgs,
+    "tvt_l2norm_bwd": L2NormArgs,
     "tvt_pyramid_head": PyramidHeadArgs,
     "tvt_colsum": ColsumArgs,
     "tvt_split_f32": SplitArgs,

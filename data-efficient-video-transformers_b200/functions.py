@@ -12,6 +12,7 @@ with a hand-scheduled backward (fused epilogues, recomputed dropout masks, no te
   DistillLossFn   BCE + CE(argmax teacher) + KL               src/models/frame_transformer.py:250-257
   PyramidHeadFn   sigmoid, mean over scales, BCE              src/models/TPN.py:98,112
   SpatialPoolFn   AvgPool2d to 1x1 of a CNN feature map       src/models/TPN.py:5,19,32
+  CollabMixFn / CollabGateFn / L2NormFn   the glue of collaborative gating   src/models/collabgating.py:35-53,66-69,83-85
 
 Tokens are kept batch-major inside the package: a (B, S, d) sequence batch is a [B*S, d] matrix.
 """
@@ -554,3 +555,46 @@ class SpatialPoolFn(torch.autograd.Function):
         dx = torch.empty(shape, dtype=dtype, device=dpooled.device)
         ops.spatial_pool_bwd(dpooled.contiguous().float(), dx, 0)
         return dx
+
+
+class CollabMixFn(torch.autograd.Function):
+    """T_i = (E-1) C_i + sum_{j>i} C_j + sum_{j<i} PC_j over stacked experts (collabgating.py:35-43,49)."""
+
+    @staticmethod
+    def forward(ctx, c, pc):
+        return ops.collab_mix_fwd(c.contiguous(), pc.contiguous())
+
+    @staticmethod
+    def backward(ctx, dt):
+        return ops.collab_mix_bwd(dt.contiguous())
+
+
+class CollabGateFn(torch.autograd.Function):
+    """g = sum_i C_i * sigmoid(C_i + A_i) (ContextGating's GLU, collabgating.py:83-85, summed over experts :50)."""
+
+    @staticmethod
+    def forward(ctx, c, a):
+        c, a = c.contiguous(), a.contiguous()
+        ctx.save_for_backward(c, a)
+        return ops.collab_gate_fwd(c, a)
+
+    @staticmethod
+    def backward(ctx, dg):
+        c, a = ctx.saved_tensors
+        return ops.collab_gate_bwd(c, a, dg.contiguous())
+
+
+class L2NormFn(torch.autograd.Function):
+    """y = F.normalize(x) per row (GatedEmbeddingUnit, collabgating.py:66-69); y fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y, inv = ops.l2norm_fwd(x.contiguous())
+        ctx.save_for_backward(y, inv)
+        ctx.in_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        return ops.l2norm_bwd(dy.contiguous().float(), y, inv, ctx.in_dtype)

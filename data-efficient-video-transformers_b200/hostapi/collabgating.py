@@ -8,14 +8,15 @@ THREE tensor-core GEMMs on stacked rows:
                        on its work list (collabgating.py:49)                                   [(E-1)*N, 2048]
     A  = P(T)          with T_i = (E-1) C_i + sum_{j>i} C_j + sum_{j<i} PC_j                    [E*N, 2048]
 then out = sum_i C_i * sigmoid(C_i + A_i)  (ContextGating's GLU, :83-85) and normalize(geu.fc(out)).
+Everything between the GEMMs is one fused kernel each, forward and backward (csrc/collab.cu): the nearest-neighbour stretch +
+cast of the inputs (``tvt_stretch_cast``), T (``tvt_collab_mix``), the gate sum (``tvt_collab_gate``) and the L2
+normalisation (``tvt_l2norm``) - no eager torch arithmetic is left on the path.
 Parameter names / shapes are the reference's (``projection.*``, ``geu.fc.*``)."""
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
-from ..functions import LinearFn
-from .common import to_act
+from ..functions import CollabGateFn, CollabMixFn, L2NormFn, LinearFn
 
 
 class GatedEmbeddingUnit(nn.Module):
@@ -51,22 +52,24 @@ class CollaborativeGating(nn.Module):
         if isinstance(xs[0], (list, tuple)):
             xs = self.from_nested(xs)
         E = len(xs)
-        if E < 2:
-            raise ValueError("CollaborativeGating needs at least two experts")
+        if E < 2 or E > 8:
+            raise ValueError("CollaborativeGating needs between two and eight experts")
         B, S = xs[0].shape[:2]
         N = B * S
         m = self.mode
+        D = self.proj_input
+        if not xs[0].is_cuda:
+            raise ops.TvtError("input tensor is not on a CUDA device: this path has no CPU implementation")
         P = lambda rows: LinearFn.apply(m, rows, self.projection.weight, self.projection.bias)
-        act = lambda t: t.contiguous() if m.fp32 else t.to(torch.bfloat16).contiguous()   # differentiable cast to the mode's dtype
-        X = torch.cat([to_act(m, self.pad(x).reshape(N, -1)) for x in xs], dim=0)         # [E*N, 2048]
-        C = P(X)
-        PC = P(C[: (E - 1) * N].contiguous())                                             # experts 0..E-2, projected twice
-        Cs, PCs = C.float().view(E, N, -1), PC.float().view(E - 1, N, -1)
-        suffix = torch.flip(torch.cumsum(torch.flip(Cs, [0]), 0), [0])                     # sum_{j>=i} C_j
-        prefix = torch.cumsum(PCs, 0)                                                      # sum_{j<=i} PC_j
-        T = (E - 1) * Cs + (suffix - Cs)
-        T[1:] = T[1:] + prefix
-        A = P(act(T.view(E * N, -1))).float().view(E, N, -1)
-        gated = (Cs * torch.sigmoid(Cs + A)).sum(0)                                        # sum_i GLU(cat(C_i, C_i + A_i))
-        out = LinearFn.apply(m, act(gated), self.geu.fc.weight, self.geu.fc.bias).float()
-        return F.normalize(out).view(B, S, -1)
+        # every expert stretched to 2048 (nearest neighbour, collabgating.py:12-16) and cast, straight into its slice of the
+        # stacked operand: no index_select / cat / cast passes
+        X = torch.empty(E * N, D, dtype=m.dtype, device=xs[0].device)
+        for e, x in enumerate(xs):
+            ops.stretch_cast(x.reshape(N, -1), X[e * N:(e + 1) * N])
+        C = P(X)                                                           # [E*N, 2048]
+        PC = P(C[: (E - 1) * N])                                           # experts 0..E-2, projected twice (:49)
+        T = CollabMixFn.apply(C.view(E, N, D), PC.view(E - 1, N, D))       # pairwise-sum bookkeeping, one pass
+        A = P(T.view(E * N, D))
+        gated = CollabGateFn.apply(C.view(E, N, D), A.view(E, N, D))       # sum_i GLU(cat(C_i, C_i + A_i))
+        out = LinearFn.apply(m, gated, self.geu.fc.weight, self.geu.fc.bias)
+        return L2NormFn.apply(out).view(B, S, -1)

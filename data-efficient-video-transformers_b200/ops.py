@@ -523,3 +523,73 @@ def feature_augment(x, d_out=None, *, p_drop=0.0, p_noise=0.0, noise_std=0.1 ** 
     a = capi.FeatureAugmentArgs(_p(x), _p(y), x.numel() // d_in, d_in, d_out, p_drop, p_noise, noise_std, seed, _dt(y))
     capi.call("tvt_feature_augment", a, _stream())
     return y
+
+
+# ------------------------------------------------------------------------------------------ collaborative gating glue
+def stretch_cast(x, out):
+    """out[:, :] (rows of a [rows, 2048] slice, any row pitch) = nearest-neighbour stretch of x [rows, d_in] fp32."""
+    _cuda(x, out)
+    if x.dtype != torch.float32:
+        x = x.float()
+    x = x.contiguous()
+    a = capi.StretchCastArgs(_p(x), _p(out), x.shape[0], x.shape[1], out.shape[1], _rowmajor(out), _dt(out), 0)
+    capi.call("tvt_stretch_cast", a, _stream())
+
+
+def _collab(name, E, rows, d, dtype, **ptrs):
+    a = capi.CollabArgs()
+    for k, t in ptrs.items():
+        setattr(a, k, _p(t))
+    a.rows, a.d, a.experts, a.dtype = rows, d, E, dtype
+    capi.call(name, a, _stream())
+
+
+def collab_mix_fwd(c, pc):
+    """c [E, N, D], pc [E-1, N, D] -> T [E, N, D] (see tvt_collab_mix_fwd)."""
+    _cuda(c, pc)
+    E, N, D = c.shape
+    out = torch.empty_like(c)
+    _collab("tvt_collab_mix_fwd", E, N, D, _dt(c), c=c, pc=pc, out=out)
+    return out
+
+
+def collab_mix_bwd(dt):
+    E, N, D = dt.shape
+    dc = torch.empty_like(dt)
+    dpc = torch.empty(E - 1, N, D, dtype=dt.dtype, device=dt.device)
+    _collab("tvt_collab_mix_bwd", E, N, D, _dt(dt), dout=dt, dc=dc, dpc=dpc)
+    return dc, dpc
+
+
+def collab_gate_fwd(c, a):
+    _cuda(c, a)
+    E, N, D = c.shape
+    out = torch.empty(N, D, dtype=c.dtype, device=c.device)
+    _collab("tvt_collab_gate_fwd", E, N, D, _dt(c), c=c, a=a, out=out)
+    return out
+
+
+def collab_gate_bwd(c, a, dg):
+    E, N, D = c.shape
+    dc, da = torch.empty_like(c), torch.empty_like(a)
+    _collab("tvt_collab_gate_bwd", E, N, D, _dt(c), c=c, a=a, dout=dg, dc=dc, da=da)
+    return dc, da
+
+
+def l2norm_fwd(x, eps=1e-12):
+    """x [rows, d] (bf16 / fp32) -> (y fp32 = x / max(||x||, eps), inv_norm [rows])."""
+    _cuda(x)
+    rows, d = x.shape
+    y = torch.empty(rows, d, dtype=torch.float32, device=x.device)
+    inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+    a = capi.L2NormArgs(_p(x), _p(y), _p(inv), None, None, rows, d, eps, _dt(x))
+    capi.call("tvt_l2norm_fwd", a, _stream())
+    return y, inv
+
+
+def l2norm_bwd(dy, y, inv, dtype, eps=1e-12):
+    rows, d = y.shape
+    dx = torch.empty(rows, d, dtype=dtype, device=y.device)
+    a = capi.L2NormArgs(None, _p(y), _p(inv), _p(dy), _p(dx), rows, d, eps, _dt(dx))
+    capi.call("tvt_l2norm_bwd", a, _stream())
+    return dx

@@ -40,6 +40,9 @@ typedef enum {
 typedef enum { TVT_BF16 = 0, TVT_F32 = 1, TVT_F64 = 2 /* evaluation labels only */ } tvt_dtype;
 typedef enum { TVT_ACT_NONE = 0, TVT_ACT_RELU = 1, TVT_ACT_GELU = 2 } tvt_act;
 
+/* Note on SURVEY.md section 8(b2), which sketched `(args, workspace, workspace_bytes, stream)` signatures: no entry point
+ * takes a workspace.  Every kernel either needs none or accumulates into caller-owned output buffers (split-K partial
+ * sums meet in fp32 atomics on `out_f32`), so the caller (PyTorch's caching allocator) still owns every byte. */
 TVT_API const char* tvt_last_error(void);
 TVT_API int tvt_version(void);
 /* TVT_OK when the current CUDA device is a B200-class part (compute capability 10.x). */
@@ -445,6 +448,58 @@ typedef struct {
   int32_t dtype;
 } tvt_cls_sum_args;
 TVT_API int tvt_cls_sum_fwd(const tvt_cls_sum_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Collaborative gating fusion (src/models/collabgating.py:17-56,59-87): the
+ * elementwise / row-wise work between the three stacked projection GEMMs (tvt_gemm), forward and backward.
+ *   tvt_stretch_cast     F.interpolate(x, 2048) nearest-neighbour stretch of a narrow expert (collabgating.py:12-16),
+ *                        y[r, i] = x[r, floor(i * d_in / d_out)], cast to the activation dtype, written at row pitch ld_out
+ *   tvt_collab_mix_fwd   T_i = (E-1) C_i + sum_{j>i} C_j + sum_{j<i} PC_j  (the pairwise sums t_i = c_i + c_j of :35-43 with
+ *                        the re-projected experts of :49);  _bwd:  dC_j = (E-1) dT_j + sum_{i<j} dT_i,  dPC_j = sum_{i>j} dT_i
+ *   tvt_collab_gate_fwd  g = sum_i C_i * sigmoid(C_i + A_i)  (ContextGating's GLU :83-85, summed over experts :50);
+ *                        _bwd: dC_i, dA_i from dg
+ *   tvt_l2norm_fwd/_bwd  F.normalize of GatedEmbeddingUnit (:66-69): y = x / max(||x||, eps) per row (y, dy fp32)
+ * c / a / out / dc / da: [experts, rows, d] (pc / dpc: [experts - 1, rows, d]; gate out / dout: [rows, d]), contiguous,
+ * of `dtype`. */
+typedef struct {
+  const float* x;     /* [rows, d_in] fp32 */
+  void* y;            /* [rows, ld_out] of out_dtype; columns [0, d_out) written */
+  int64_t rows, d_in, d_out, ld_out;
+  int32_t out_dtype;
+  int32_t reserved;
+} tvt_stretch_cast_args;
+TVT_API int tvt_stretch_cast(const tvt_stretch_cast_args* args, void* stream);
+
+typedef struct {
+  const void* c;      /* C  */
+  const void* pc;     /* PC (mix) */
+  const void* a;      /* A  (gate) */
+  void* out;          /* T (mix fwd) or g (gate fwd) */
+  const void* dout;   /* dT (mix bwd) or dg (gate bwd) */
+  void* dc;
+  void* dpc;          /* mix bwd */
+  void* da;           /* gate bwd */
+  int64_t rows, d;
+  int32_t experts;
+  int32_t dtype;
+} tvt_collab_args;
+TVT_API int tvt_collab_mix_fwd(const tvt_collab_args* args, void* stream);
+TVT_API int tvt_collab_mix_bwd(const tvt_collab_args* args, void* stream);
+TVT_API int tvt_collab_gate_fwd(const tvt_collab_args* args, void* stream);
+TVT_API int tvt_collab_gate_bwd(const tvt_collab_args* args, void* stream);
+
+typedef struct {
+  const void* x;      /* fwd: [rows, d] of dtype */
+  float* y;           /* [rows, d] fp32: written by fwd, read by bwd */
+  float* inv_norm;    /* [rows] fp32: 1 / max(||x||, eps), written by fwd, read by bwd */
+  const float* dy;    /* bwd */
+  void* dx;           /* bwd: [rows, d] of dtype */
+  int64_t rows, d;
+  float eps;
+  int32_t dtype;
+} tvt_l2norm_args;
+TVT_API int tvt_l2norm_fwd(const tvt_l2norm_args* args, void* stream);
+TVT_API int tvt_l2norm_bwd(const tvt_l2norm_args* args, void* stream);
 
 /* Loader-side feature path on the GPU (src/dataloaders/MMX_Temporal_dl.py:167-181), one pass per expert tensor:
  *   zero-pad each [1, D_in] feature vector to D_out columns (ConstantPad1d to 2048, :167-169; d_out == d_in skips it),

@@ -42,7 +42,7 @@ def test_ctypes_structs_match_c_layout(capi):
     # irregular names
     fix = {"LayerNormFwdArgs": "tvt_layernorm_fwd_args", "LayerNormBwdArgs": "tvt_layernorm_bwd_args",
            "SpatialPoolArgs": "tvt_spatial_pool_args", "SplitArgs": "tvt_split_args", "ColsumArgs": "tvt_colsum_args",
-           "PosencArgs": "tvt_posenc_args"}
+           "PosencArgs": "tvt_posenc_args", "L2NormArgs": "tvt_l2norm_args", "Split3Args": "tvt_split3_args"}
     cnames.update(fix)
     body = "\n".join(f'  printf("{py} %zu\\n", sizeof({c}));' for py, c in cnames.items())
     prog = f'#include <stdio.h>\n#include "tvt.h"\nint main(void) {{\n{body}\n  return 0;\n}}\n'
