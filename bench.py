@@ -183,7 +183,7 @@ def time_oracle(w, sample_clips, steps, warmup):
 def run_reference(args, w, rank):
     if rank != 0:
         return
-    sample = args.cpu_clips or max(1, min(w["batch"], int(2.5e11 / flops_per_clip(w)) or 1))
+    sample = args.cpu_clips or max(1, min(w["batch"], int(1.2e12 / flops_per_clip(w)) or 1))   # ~2 s of CPU work per step at C5
     cps, dt, cores = time_oracle(w, sample, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "train clips/sec fwd+bwd", "value": round(cps, 3), "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
