@@ -282,7 +282,7 @@ def run_tvt(w, args, ctx, steps, warmup, sample_clocks=False, graph=None):
     graph = args.graph if graph is None else graph
     model = build_model(w, B, args.precision, args.dropout, dev)
     trainable = [p for p in model.parameters() if p.requires_grad]
-    reducer = ddp.GradBucketReducer(trainable, bucket_bytes=32 << 20, average=False)
+    reducer = ddp.GradBucketReducer(trainable, bucket_bytes=int(os.environ.get("TVT_BUCKET_MB", "32")) << 20, average=False)
     student = model.student if w["teacher"] else model
     # flat-bucket AdamW: one launch per gradient bucket, 1 / world averaging and bf16 weight planes fused
     opt = optim.FlatOptimizer(reducer, modes=[student.mode], kind="adamw", lr=1e-4, weight_decay=0.01)
