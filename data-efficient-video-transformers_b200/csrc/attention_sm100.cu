@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <type_traits>
 #include <set>
 
 #include "tvt_common.cuh"
@@ -366,6 +367,9 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
   const int tk = p.Sk - n_keys;                    // tail keys (per thread)
   const int n_mma = (n_keys + 15) & ~15;
   const float sl2 = p.scale * kLog2e;
+  // 32-bit shared-space addresses of the tiles: the CUDA-core paths below read them with ld.shared (a generic-pointer
+  // dereference costs 64-bit address arithmetic per load, which was a fifth of this kernel's instructions)
+  const uint32_t sQ_s = smem_u32(sQ), sK_s = smem_u32(sK), sV_s = smem_u32(sV), tail_p_s = smem_u32(tail_p);
 
   if (issuer) {
     mbar_init(smem_u32(bar_kv), 1);
@@ -428,11 +432,11 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
       for (int c = 0; c < 8; ++c) {
         float qf[8], kf[8];
         Vec16<__nv_bfloat16>::unpack(qraw[c], qf);
-        Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(tid, c)), kf);
+        Vec16<__nv_bfloat16>::unpack(lds128(sK_s + sw128(tid, c)), kf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s0 += qf[i] * kf[i];
         if (tid < tk) {
-          Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(128 + tid, c)), kf);
+          Vec16<__nv_bfloat16>::unpack(lds128(sK_s + sw128(128 + tid, c)), kf);
 #pragma unroll
           for (int i = 0; i < 8; ++i) s1 += qf[i] * kf[i];
         }
@@ -457,9 +461,9 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
         for (int j = warp * 4 + (lane >> 3); j < p.Sk; j += 16) {
-          const float pj = tail_p[j];
+          const float pj = lds_f32(tail_p_s + 4 * j);
           float vf[8];
-          Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(j, ch)), vf);
+          Vec16<__nv_bfloat16>::unpack(lds128(sV_s + sw128(j, ch)), vf);
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, vf[i], acc[i]);
         }
@@ -499,8 +503,8 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float qf[8], kf[8];
-          Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sQ + sw128(tid, c)), qf);
-          Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sK + sw128(128 + t, c)), kf);
+          Vec16<__nv_bfloat16>::unpack(lds128(sQ_s + sw128(tid, c)), qf);
+          Vec16<__nv_bfloat16>::unpack(lds128(sK_s + sw128(128 + t, c)), kf);
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc += qf[i] * kf[i];
         }
@@ -540,14 +544,15 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
       }
     }
     // pass 2: P (bf16) into the A-operand tiles, 32 columns per TMEM round trip
-    auto emit16 = [&](int c0, const uint32_t* r) {
+    auto emit16 = [&](int c0, const uint32_t* r, auto full_tag) {
+      constexpr bool kFull = decltype(full_tag)::value;   // full blocks carry no per-key select (two instructions per key otherwise)
       uint32_t packed[8];
       float e[16];
-      const int lim = n_keys - c0;               // >= 16: full block
+      const int lim = n_keys - c0;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         e[i] = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, -mxs));
-        if (lim < 16) e[i] = i < lim ? e[i] : 0.0f;   // padding keys of the last block
+        if constexpr (!kFull) e[i] = i < lim ? e[i] : 0.0f;   // padding keys of the last block
       }
 #pragma unroll
       for (int i = 0; i < 16; i += 4) sum += (e[i] + e[i + 1]) + (e[i + 2] + e[i + 3]);
@@ -559,17 +564,26 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
       }
 #pragma unroll
       for (int i = 0; i < 16; i += 2) packed[i >> 1] = pack_bf16x2(e[i], e[i + 1]);
-      const uint32_t blk = smem_u32(c0 < 64 ? sQ : sK);
+      const uint32_t blk = c0 < 64 ? sQ_s : sK_s;
       const int ch = (c0 & 63) >> 3;
       sts128(blk + sw128(tid, ch), packed[0], packed[1], packed[2], packed[3]);
       sts128(blk + sw128(tid, ch + 1), packed[4], packed[5], packed[6], packed[7]);
     };
+    {
+      int c0 = 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < n_mma; c0 += 16) {   // one copy of the body: the kernel is instruction-cache sensitive
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
-      tmem_ld_wait_dep(r);
-      emit16(c0, r);
+      for (; c0 + 16 <= n_keys; c0 += 16) {    // one copy of the full-block body: the kernel is instruction-cache sensitive
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
+        tmem_ld_wait_dep(r);
+        emit16(c0, r, std::true_type{});
+      }
+      if (c0 < n_mma) {                         // the partial last block (never at S = 129: 128 main keys)
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + lane_addr + c0, r);
+        tmem_ld_wait_dep(r);
+        emit16(c0, r, std::false_type{});
+      }
     }
     fence_proxy_async_smem();
   }
@@ -606,7 +620,7 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float vf[8];
-              Vec16<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(sV + sw128(128 + t, (c0 >> 3) + g)), vf);
+              Vec16<__nv_bfloat16>::unpack(lds128(sV_s + sw128(128 + t, (c0 >> 3) + g)), vf);
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[8 * g + i] += st[t] * vf[i];
             }
