@@ -29,7 +29,9 @@ class GemmArgs(C.Structure):
                 ("relu_mask", vp), ("mask_dtype", i32), ("ld_mask", i64), ("gelu_gate", vp), ("gate_dtype", i32),
                 ("ld_gate", i64), ("dropout_p", f32), ("dropout_seed", u64), ("out_preact", vp),
                 ("preact_dtype", i32), ("ld_preact", i64), ("out_f32", vp), ("ld_f32", i64), ("atomic_out", i32),
-                ("out_bf16", vp), ("out_bf16_lo", vp), ("ld_bf16", i64)]
+                ("out_bf16", vp), ("out_bf16_lo", vp), ("ld_bf16", i64),
+                ("ln_in_stats", vp), ("ln_in_c", vp), ("ln_res_stats", vp), ("ln_res_gamma", vp), ("ln_res_beta", vp),
+                ("stats_out", vp), ("ln_dim", i64), ("ln_eps", f32), ("reserved", i32)]
 
 
 class LayerNormFwdArgs(C.Structure):
@@ -193,7 +195,8 @@ ENTRY_POINTS = {
     "tvt_eval_readout": EvalReadoutArgs,
     "tvt_feature_augment": FeatureAugmentArgs,
 }
-PLAIN_SYMBOLS = ("tvt_last_error", "tvt_version", "tvt_device_check", "tvt_set_seed_source", "tvt_step_counter_advance")
+PLAIN_SYMBOLS = ("tvt_last_error", "tvt_version", "tvt_device_check", "tvt_set_seed_source", "tvt_step_counter_advance",
+                 "tvt_gemm_ln_fold_supported")
 
 _lib = None
 launches = 0  # number of kernel-launching entry-point calls made through this module (bench.py reads it)
@@ -216,6 +219,8 @@ def load():
     lib.tvt_set_seed_source.argtypes = [vp]
     lib.tvt_step_counter_advance.restype = C.c_int
     lib.tvt_step_counter_advance.argtypes = [vp, C.c_int, vp]
+    lib.tvt_gemm_ln_fold_supported.restype = C.c_int
+    lib.tvt_gemm_ln_fold_supported.argtypes = [i64, i64, i64]
     for name, st in ENTRY_POINTS.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

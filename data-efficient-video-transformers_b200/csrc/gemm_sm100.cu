@@ -42,6 +42,9 @@ struct Params {
   float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed; const unsigned long long* seed_src;
   unsigned drop_rk[kDropoutRounds];   // per-round keys of the dropout hash (host-computed: they are launch constants)
   void* out_preact; int preact_f32; long long ld_preact;
+  // LayerNorm folded into the epilogue (see tvt_gemm_args): raw (sum, sum of squares) rows, 1 / ln_dim, eps
+  const float* ln_in_stats; const float* ln_in_c; const float* ln_res_stats; const float* ln_res_gamma; const float* ln_res_beta;
+  float* stats_out; float ln_inv_d, ln_eps;
   float* out_f32; long long ld_f32; int atomic_out;
   __nv_bfloat16* out_bf16; __nv_bfloat16* out_bf16_lo; long long ld_bf16;
   unsigned mn_lbo, mn_sbo;  // MN-major descriptor strides (bring-up knob, see tvt_debug_set_mn_desc)
@@ -53,13 +56,13 @@ static int g_dbg = 0;
 static int g_pair = [] { const char* e = getenv("TVT_GEMM_PAIR"); return e ? atoi(e) : 1; }();   // bring-up knob: 0 = never use the CTA-pair kernels
 static long long g_fast_fallbacks = 0;   // fast-path launches that had no exact-stage kernel (see tvt_gemm)
 
-template <int BN, int kPlanes, bool kSide, bool kFastEpi, bool kCta2 = false>
+template <int BN, int kPlanes, bool kSide, bool kFastEpi, bool kCta2 = false, int kSlabs = 1>
 struct Cfg {
   static constexpr int kAPlane = BM * BK * 2;
   static constexpr int kBRows = kCta2 ? BN / 2 : BN;   // a CTA pair splits the B tile between its two CTAs
   static constexpr int kBPlane = kBRows * BK * 2;
   static constexpr int kStageBytes = kPlanes * (kAPlane + kBPlane);
-  static constexpr int kEpiWarpBytes = kFastEpi ? kBiasSlab : kEpiStageBytes;
+  static constexpr int kEpiWarpBytes = kFastEpi ? kSlabs * kBiasSlab : kEpiStageBytes;   // fast kernels: bias (+ c | gamma, beta) slabs
   static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
   static constexpr int kSideSlots = BN / 128;  // one per two 32-column chunk steps of the epilogue warps
   static constexpr int kSideBytes = kSide ? kSideSlots * kSideSlotBytes : 0;
@@ -105,6 +108,13 @@ __device__ __forceinline__ void store8(void* base, int is_f32, long long off, co
 // kEpiFast + a stage mask (kStRelu ...) is a kernel with exactly those stages compiled in, unconditionally.
 enum { kEpiGeneric = 0, kEpiAtomic = 2, kEpiFast = 16 };
 enum { kStRelu = 1, kStMask = 2, kStDrop = 4, kStRes = 8 };
+// LayerNorm-folded inference epilogues (tvt_gemm_args.ln_*): kStLnIn = the A operand is a PRE-norm tensor (per-row rstd / mean
+// and the per-column c vector rebuild LN(y) W^T); kStLnRes = the residual is LN(side operand), recomputed; kStStats = accumulate
+// the output row's (sum, sum of squares) for the next LayerNorm.  Bits above kSideLdg.
+enum { kStLnIn = 64, kStLnRes = 128, kStStats = 256 };
+__host__ __device__ constexpr int epi_slabs(int kEpi) {
+  return kEpi >= 16 ? ((((kEpi - 16) & kStLnRes) != 0) ? 3 : ((((kEpi - 16) & kStLnIn) != 0) ? 2 : 1)) : 1;
+}
 __host__ __device__ constexpr bool is_fast(int kEpi) { return kEpi >= kEpiFast; }
 __host__ __device__ constexpr bool has_stage(int kEpi, int st) { return kEpi >= kEpiFast && ((kEpi - kEpiFast) & st) != 0; }
 // Fast kernels with a bf16 side operand (relu mask or residual) fetch it one of two ways:
@@ -251,17 +261,34 @@ __device__ __forceinline__ void stg256(void* ptr, const uint32_t* r) {
 // relu mask, dropout, bf16 residual, packed to bf16.  scale = alpha * dropout_scale and bias' = bias *
 // dropout_scale are folded by the caller (every stage before the residual is positively homogeneous), side[]
 // holds the row's 32 mask or residual values.  About 320 instructions with every stage on.
+// Per-row scalars of the LayerNorm-folded stages (thread == row): rs / rb = rstd and -mean * rstd of the A operand's row
+// (kStLnIn), ls / lb the same for the residual's row (kStLnRes); sum / sq accumulate the output row (kStStats).
+struct RowLn { float rs, rb, ls, lb, sum, sq; };
+
 template <int kEpi>
 __device__ __forceinline__ void epilogue_fast(const Params& p, float scale, uint32_t bias_s, uint32_t e4_lo, uint32_t e4_hi,
-                                              const uint32_t (&r)[32], const uint32_t (&side)[16], uint32_t (&out)[16]) {
+                                              const uint32_t (&r)[32], const uint32_t (&side)[16], uint32_t (&out)[16], RowLn& ln) {
   float v[32];
+  if constexpr (has_stage(kEpi, kStLnIn)) {
+    const float sc = scale * ln.rs;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const uint4 b = lds128(bias_s + 16 * q);   // broadcast read of the warp's bias slab
-    v[4 * q] = fmaf(__uint_as_float(r[4 * q]), scale, __uint_as_float(b.x));
-    v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), scale, __uint_as_float(b.y));
-    v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), scale, __uint_as_float(b.z));
-    v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), scale, __uint_as_float(b.w));
+    for (int q = 0; q < 8; ++q) {
+      const uint4 b = lds128(bias_s + 16 * q);               // b'
+      const uint4 c = lds128(bias_s + kBiasSlab + 16 * q);   // c = rowsum(W diag(gamma))
+      v[4 * q] = fmaf(__uint_as_float(r[4 * q]), sc, fmaf(ln.rb, __uint_as_float(c.x), __uint_as_float(b.x)));
+      v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), sc, fmaf(ln.rb, __uint_as_float(c.y), __uint_as_float(b.y)));
+      v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), sc, fmaf(ln.rb, __uint_as_float(c.z), __uint_as_float(b.z)));
+      v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), sc, fmaf(ln.rb, __uint_as_float(c.w), __uint_as_float(b.w)));
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 b = lds128(bias_s + 16 * q);   // broadcast read of the warp's bias slab
+      v[4 * q] = fmaf(__uint_as_float(r[4 * q]), scale, __uint_as_float(b.x));
+      v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), scale, __uint_as_float(b.y));
+      v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), scale, __uint_as_float(b.z));
+      v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), scale, __uint_as_float(b.w));
+    }
   }
   if constexpr (has_stage(kEpi, kStRelu)) {
 #pragma unroll
@@ -287,14 +314,35 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, float scale, uint
     }
   }
   if constexpr (has_stage(kEpi, kStRes)) {
+    if constexpr (has_stage(kEpi, kStLnRes)) {   // residual = LN(side row): ((y - mean) * rstd) * gamma + beta
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      v[2 * i] += __uint_as_float(side[i] << 16);
-      v[2 * i + 1] += __uint_as_float(side[i] & 0xFFFF0000u);
+      for (int q = 0; q < 8; ++q) {
+        const uint4 g = lds128(bias_s + kBiasSlab + 16 * q), b = lds128(bias_s + 2 * kBiasSlab + 16 * q);
+        const float y0 = __uint_as_float(side[2 * q] << 16), y1 = __uint_as_float(side[2 * q] & 0xFFFF0000u);
+        const float y2 = __uint_as_float(side[2 * q + 1] << 16), y3 = __uint_as_float(side[2 * q + 1] & 0xFFFF0000u);
+        v[4 * q] += fmaf(fmaf(y0, ln.ls, ln.lb), __uint_as_float(g.x), __uint_as_float(b.x));
+        v[4 * q + 1] += fmaf(fmaf(y1, ln.ls, ln.lb), __uint_as_float(g.y), __uint_as_float(b.y));
+        v[4 * q + 2] += fmaf(fmaf(y2, ln.ls, ln.lb), __uint_as_float(g.z), __uint_as_float(b.z));
+        v[4 * q + 3] += fmaf(fmaf(y3, ln.ls, ln.lb), __uint_as_float(g.w), __uint_as_float(b.w));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[2 * i] += __uint_as_float(side[i] << 16);
+        v[2 * i + 1] += __uint_as_float(side[i] & 0xFFFF0000u);
+      }
     }
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  if constexpr (has_stage(kEpi, kStStats)) {   // statistics of the STORED (bf16-rounded) row: what the next LayerNorm would read
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a = __uint_as_float(out[i] << 16), b = __uint_as_float(out[i] & 0xFFFF0000u);
+      ln.sum += a + b;
+      ln.sq = fmaf(a, a, fmaf(b, b, ln.sq));
+    }
+  }
 }
 
 template <int kEpi>
@@ -350,7 +398,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
             const __grid_constant__ CUtensorMap tmSide, const Params p) {
   constexpr bool kSide = has_side(kEpi);
-  using C = Cfg<BN, kPlanes, kSide, is_fast(kEpi), kCta2>;
+  using C = Cfg<BN, kPlanes, kSide, is_fast(kEpi), kCta2, epi_slabs(kEpi)>;
   constexpr int kCtas = kCta2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -572,6 +620,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (has_next) bias_nx = load_bias((wn % num_n) * BN + half * (BN / 2));
         }
         bias_valid = has_next;
+        RowLn ln{1.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f};
+        if constexpr (has_stage(kEpi, kStLnIn) || has_stage(kEpi, kStLnRes)) {
+          // the extra per-column vectors of the folded LayerNorm (c | gamma, beta) next to the bias slab, and this row's
+          // statistics turned into (rstd, -mean * rstd)
+          if (4 * lane < BN / 2) {
+            const int c = colbase + 4 * lane;
+            const float* v1 = has_stage(kEpi, kStLnIn) ? p.ln_in_c : p.ln_res_gamma;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = c < p.N ? __ldg(reinterpret_cast<const float4*>(v1 + c)) : z;
+            sts128(bias_addr + kBiasSlab + 16 * lane, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w));
+            if constexpr (has_stage(kEpi, kStLnRes)) {
+              const float4 b = c < p.N ? __ldg(reinterpret_cast<const float4*>(p.ln_res_beta + c)) : z;
+              sts128(bias_addr + 2 * kBiasSlab + 16 * lane, __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+            }
+          }
+          if (row < p.M) {
+            const float2 st = __ldg(reinterpret_cast<const float2*>((has_stage(kEpi, kStLnIn) ? p.ln_in_stats : p.ln_res_stats) + 2 * row));
+            const float mean = st.x * p.ln_inv_d;
+            const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, st.y * p.ln_inv_d), 0.0f) + p.ln_eps);
+            if constexpr (has_stage(kEpi, kStLnIn)) { ln.rs = rstd; ln.rb = -mean * rstd; }
+            else { ln.ls = rstd; ln.lb = -mean * rstd; }
+          }
+        }
         __syncwarp();
         uint32_t side[16];
         const __nv_bfloat16* side_row = nullptr;
@@ -618,7 +689,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const unsigned long long e4 = (static_cast<unsigned long long>(row) * p.N + col0) >> 2;   // multiple of 8: + q never carries
           uint32_t out[16];
           epilogue_fast<kEpi>(p, scale, bias_addr + c * 128, static_cast<uint32_t>(e4),
-                              static_cast<uint32_t>(e4 >> 32) ^ static_cast<uint32_t>(mix_seed(p.dropout_seed, p.seed_src) >> 32), r, side, out);
+                              static_cast<uint32_t>(e4 >> 32) ^ static_cast<uint32_t>(mix_seed(p.dropout_seed, p.seed_src) >> 32), r, side, out, ln);
           release_slot();
           if constexpr (side_ldg(kEpi)) {
             if (c + 1 < BN / 64 && col0 + 32 < p.N && row < p.M) { ldg256(side_row + col0 + 32, side); ldg256(side_row + col0 + 48, side + 8); }
@@ -627,6 +698,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __nv_bfloat16* orow = p.out_bf16 + row * p.ld_bf16 + col0;
             stg256(orow, out);
             stg256(orow + 16, out + 8);
+          }
+        }
+        if constexpr (has_stage(kEpi, kStStats)) {
+          if (row_ok) {
+            atomicAdd(p.stats_out + 2 * row, ln.sum);
+            atomicAdd(p.stats_out + 2 * row + 1, ln.sq);
           }
         }
         sphase ^= 1;
@@ -778,7 +855,7 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
 
 template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi, bool kCta2 = false>
 static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) {
-  using C = Cfg<BN, kPlanes, has_side(kEpi), is_fast(kEpi), kCta2>;
+  using C = Cfg<BN, kPlanes, has_side(kEpi), is_fast(kEpi), kCta2, epi_slabs(kEpi)>;
   CUtensorMap tmA, tmAlo, tmB, tmBlo, tmSide;
   int rc;
   auto mapA = [&](CUtensorMap* m, const void* ptr) {
@@ -850,6 +927,18 @@ extern "C" void tvt_debug_set_epilogue(int mode) { tvt::gemm::g_dbg = mode; }
 extern "C" void tvt_debug_set_pair(int on) { tvt::gemm::g_pair = on; }
 extern "C" long long tvt_debug_gemm_fast_fallbacks() { return tvt::gemm::g_fast_fallbacks; }
 
+// 1 when tvt_gemm would run an [m, n, k] bf16 forward GEMM (K-major operands, no split-K) on the CTA-pair [256 x 256] tiles, i.e.
+// when the LayerNorm-folded epilogues are available for it (the same selection as in tvt_gemm below).
+extern "C" int tvt_gemm_ln_fold_supported(int64_t m, int64_t n, int64_t k) {
+  if (m <= 0 || n <= 0 || k <= 0 || n % 32 != 0 || k % 8 != 0 || !tvt::gemm::g_pair) return 0;
+  const long long nsm = tvt::num_sms(), kb = (k + tvt::gemm::BK - 1) / tvt::gemm::BK, m_tiles = (m + 127) / 128;
+  const long long w256 = m_tiles * ((n + 255) / 256), w128 = m_tiles * ((n + 127) / 128);
+  const long long c256 = ((w256 + nsm - 1) / nsm) * (kb * 512 + 3000), c128 = ((w128 + nsm - 1) / nsm) * (kb * 400 + 1800);
+  if (n <= 128 || c128 < c256) return 0;
+  const long long wpair = ((m + 255) / 256) * ((n + 255) / 256), npair = nsm / 2;
+  return (wpair + npair - 1) / npair <= (w256 + nsm - 1) / nsm ? 1 : 0;
+}
+
 extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   using namespace tvt;
   TVT_REQUIRE(a != nullptr, "tvt_gemm: null args");
@@ -907,6 +996,9 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   }
   p.out_preact = a->out_preact; p.preact_f32 = a->preact_dtype == TVT_F32; p.ld_preact = a->ld_preact;
   p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32; p.atomic_out = a->atomic_out;
+  p.ln_in_stats = a->ln_in_stats; p.ln_in_c = a->ln_in_c; p.ln_res_stats = a->ln_res_stats;
+  p.ln_res_gamma = a->ln_res_gamma; p.ln_res_beta = a->ln_res_beta; p.stats_out = a->stats_out;
+  p.ln_inv_d = a->ln_dim > 0 ? 1.0f / static_cast<float>(a->ln_dim) : 0.0f; p.ln_eps = a->ln_eps;
   p.out_bf16 = (__nv_bfloat16*)a->out_bf16; p.out_bf16_lo = (__nv_bfloat16*)a->out_bf16_lo; p.ld_bf16 = a->ld_bf16;
 
   p.mn_lbo = gemm::g_mn_lbo; p.mn_sbo = gemm::g_mn_sbo; p.dbg = gemm::g_dbg;
@@ -944,6 +1036,38 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
       return gemm::launch<256, true, false, 1, gemm::kEpiAtomic, true>(a, p, s);
     }
     return gemm::dispatch_width<1, gemm::kEpiAtomic>(narrow, a, p, s);
+  }
+  const bool ln_any = a->ln_in_stats || a->ln_in_c || a->ln_res_stats || a->ln_res_gamma || a->ln_res_beta || a->stats_out;
+  if (ln_any) {
+    // LayerNorm-folded inference epilogues: CTA-pair fast kernels only (what the encoder layers' forward GEMMs use)
+    using namespace gemm;
+    TVT_REQUIRE(fast && !a->a_mn_major && !a->b_mn_major && a->dropout_p == 0.0f && !a->relu_mask && a->bias,
+                "tvt_gemm: the LayerNorm-folded epilogues need the bf16 fast path (K-major operands, bias, no dropout / mask)");
+    TVT_REQUIRE((a->ln_in_stats != nullptr) == (a->ln_in_c != nullptr), "tvt_gemm: ln_in_stats and ln_in_c go together");
+    TVT_REQUIRE((a->ln_res_stats != nullptr) == (a->ln_res_gamma != nullptr) && (a->ln_res_stats != nullptr) == (a->ln_res_beta != nullptr),
+                "tvt_gemm: ln_res_stats, ln_res_gamma and ln_res_beta go together");
+    TVT_REQUIRE(!(a->ln_in_stats && a->ln_res_stats), "tvt_gemm: ln_in and ln_res cannot be combined in one call");
+    TVT_REQUIRE(!a->ln_res_stats || a->residual, "tvt_gemm: ln_res needs the pre-norm residual tensor");
+    TVT_REQUIRE((!a->ln_in_stats && !a->ln_res_stats) || (a->ln_dim > 0 && a->ln_eps > 0.0f), "tvt_gemm: ln_dim / ln_eps missing");
+    TVT_REQUIRE(!(a->ln_in_stats && (a->residual || a->stats_out)), "tvt_gemm: ln_in supports bias (+ relu) only");
+    TVT_REQUIRE(!a->stats_out || a->residual, "tvt_gemm: stats_out is implemented for the residual-adding GEMMs");
+    TVT_REQUIRE(al16(a->ln_in_c) && al16(a->ln_res_gamma) && al16(a->ln_res_beta) && (reinterpret_cast<uintptr_t>(a->ln_in_stats) & 7) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->ln_res_stats) & 7) == 0 && a->n % 4 == 0,
+                "tvt_gemm: LayerNorm vectors must be 16-byte aligned, statistics 8-byte aligned");
+    TVT_REQUIRE(pair && !narrow, "tvt_gemm: the LayerNorm-folded epilogues are built for the CTA-pair [256 x 256] tiles (m, n too small)");
+    const bool side_ok = al32(a->residual, a->ld_residual);
+    const bool ldg = a->residual && kb_per > 16 && side_ok;
+    if (a->ln_in_stats) {
+      if (a->act == TVT_ACT_RELU) return launch<256, false, false, 1, kEpiFast + kStLnIn + kStRelu, true>(a, p, s);
+      return launch<256, false, false, 1, kEpiFast + kStLnIn, true>(a, p, s);
+    }
+    TVT_REQUIRE(a->act == TVT_ACT_NONE && a->stats_out, "tvt_gemm: residual GEMMs of the folded path produce statistics and have no activation");
+    if (a->ln_res_stats) {
+      if (ldg) return launch<256, false, false, 1, kEpiFast + kSideLdg + kStRes + kStLnRes + kStStats, true>(a, p, s);
+      return launch<256, false, false, 1, kEpiFast + kStRes + kStLnRes + kStStats, true>(a, p, s);
+    }
+    if (ldg) return launch<256, false, false, 1, kEpiFast + kSideLdg + kStRes + kStStats, true>(a, p, s);
+    return launch<256, false, false, 1, kEpiFast + kStRes + kStStats, true>(a, p, s);
   }
   if (fast) {
     // exact-stage kernels for the combinations the encoder layers launch (forward: both operands K-major; dgrad:

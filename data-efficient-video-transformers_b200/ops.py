@@ -55,7 +55,10 @@ def _rowmajor(t):
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm(a, b, m, n, k, *, a_lo=None, b_lo=None, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None,
          act=ACT_NONE, alpha=1.0, residual=None, relu_mask=None, gelu_gate=None, dropout_p=0.0, seed=0,
-         out_f32=None, out_bf16=None, out_bf16_lo=None, out_preact=None, splits=1, atomic=False):
+         out_f32=None, out_bf16=None, out_bf16_lo=None, out_preact=None, splits=1, atomic=False,
+         ln_in=None, ln_res=None, stats_out=None, ln_dim=0, ln_eps=1e-5):
+    """``ln_in=(stats, c)`` / ``ln_res=(stats, gamma, beta)`` / ``stats_out``: the LayerNorm-folded inference epilogues (see
+    tvt_gemm_args in include/tvt.h)."""
     _cuda(a, b, a_lo, b_lo, bias, residual, relu_mask, gelu_gate, out_f32, out_bf16, out_bf16_lo, out_preact)
     g = capi.GemmArgs()
     g.a, g.a_lo, g.b, g.b_lo = _p(a), _p(a_lo), _p(b), _p(b_lo)
@@ -78,7 +81,21 @@ def gemm(a, b, m, n, k, *, a_lo=None, b_lo=None, a_mn=False, b_mn=False, lda=Non
     g.atomic_out = int(atomic)
     if out_bf16 is not None:
         g.out_bf16, g.out_bf16_lo, g.ld_bf16 = _p(out_bf16), _p(out_bf16_lo), _rowmajor(out_bf16)
+    if ln_in is not None:
+        _cuda(*ln_in)
+        g.ln_in_stats, g.ln_in_c = _p(ln_in[0]), _p(ln_in[1])
+    if ln_res is not None:
+        _cuda(*ln_res)
+        g.ln_res_stats, g.ln_res_gamma, g.ln_res_beta = _p(ln_res[0]), _p(ln_res[1]), _p(ln_res[2])
+    if stats_out is not None:
+        _cuda(stats_out)
+        g.stats_out = _p(stats_out)
+    g.ln_dim, g.ln_eps = ln_dim, ln_eps
     capi.call("tvt_gemm", g, _stream())
+
+
+def ln_fold_supported(m, n, k):
+    return bool(capi.load().tvt_gemm_ln_fold_supported(m, n, k))
 
 
 def split_f32(x, hi, lo=None):
@@ -207,6 +224,23 @@ class Mode:
         if rows is not None:
             hi, lo = hi[rows[0]:rows[1]], lo[rows[0]:rows[1]]
         return hi, lo
+
+    def folded_weight(self, w, b, gamma, beta):
+        """A Linear fed by LayerNorm(gamma, beta), folded for the LN-free inference path (tvt_gemm_args.ln_in_*):
+        (W' = bf16(W diag(gamma)) [N, K], c = rowsum(W') fp32 [N], b' = b + W beta fp32 [N]); cached per weight version.
+        One-off host-side preparation (the teacher's weights are frozen), not part of the step."""
+        key = (id(w), "lnfold")
+        vers = (w._version, b._version, gamma._version, beta._version, id(gamma))
+        ent = self._wcache.get(key)
+        if ent is None or ent[0]() is not w or ent[1] != vers:
+            with torch.no_grad():
+                wf, g, bt = w.detach().float(), gamma.detach().float(), beta.detach().float()
+                wp = (wf * g[None, :]).to(torch.bfloat16).contiguous()
+                c = wp.float().sum(dim=1).contiguous()
+                bp = (b.detach().float() + wf @ bt).contiguous()
+            ent = (weakref.ref(w), vers, wp, c, bp)
+            self._wcache[key] = ent
+        return ent[2], ent[3], ent[4]
 
     def weight(self, w, rows=None):
         """fp32 master weight [N, K] -> cached (hi, lo) bf16 planes, refreshed when the parameter changes

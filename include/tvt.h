@@ -118,9 +118,33 @@ typedef struct {
   void* out_bf16;           /* optional [M, ld_bf16] */
   void* out_bf16_lo;        /* optional lo plane (same ld) */
   int64_t ld_bf16;
+  /* ---- LayerNorm folded into the GEMMs around it (inference: no LayerNorm kernel, its output is never materialised).
+   * A post-norm layer's LN(y) = (y - mean) * rstd * gamma + beta feeds a Linear:  LN(y) W^T + b =
+   *     rstd_m * (y (W diag(gamma))^T)[m, n]  -  rstd_m * mean_m * c_n  +  b'_n,   c = rowsum(W diag(gamma)),  b' = b + W beta,
+   * so the consumer GEMM runs on the PRE-norm tensor y with B = W diag(gamma) (caller-prepared), `bias` = b', and
+   *   ln_in_stats [M, 2] fp32 (sum, sum of squares of y's row over ln_dim columns) + ln_in_c [N]:
+   *       v = rstd_m * alpha * acc + (-mean_m rstd_m) * c_n + bias_n           (replaces v = alpha * acc + bias)
+   * and LN(y) as the RESIDUAL of the next GEMM is recomputed in its epilogue from the same y:
+   *   residual = y (pre-norm, bf16), ln_res_stats [M, 2], ln_res_gamma / ln_res_beta [N]:
+   *       v += ((residual - mean_m) * rstd_m) * gamma_n + beta_n               (replaces v += residual)
+   * The row statistics are produced by the epilogue of the GEMM that writes y:
+   *   stats_out [M, 2] fp32, caller zero-filled: (sum, sum of squares) of the final output row, atomically accumulated.
+   * bf16 fast path only (plain bf16 output, both operands K-major, n % 32 == 0); ln_dim = the normalised width, ln_eps. */
+  const float* ln_in_stats;
+  const float* ln_in_c;
+  const float* ln_res_stats;
+  const float* ln_res_gamma;
+  const float* ln_res_beta;
+  float* stats_out;
+  int64_t ln_dim;
+  float ln_eps;
+  int32_t reserved;
 } tvt_gemm_args;
 
 TVT_API int tvt_gemm(const tvt_gemm_args* args, void* stream);
+/* 1 when tvt_gemm would run this bf16 forward GEMM on the tiles that carry the LayerNorm-folded epilogues (ln_* fields), else 0:
+ * callers choose between the folded inference path and LayerNorm as a kernel of its own with it (host-only, no launch). */
+TVT_API int tvt_gemm_ln_fold_supported(int64_t m, int64_t n, int64_t k);
 
 
 /* ------------------------------------------------------------------------------------------------

@@ -672,3 +672,48 @@ def test_graphed_training_step_matches_eager_steps(api, pyramid):
     assert l1 != l2
     stepper.close()
     red.remove()
+
+
+@pytest.mark.parametrize("d,H,ff,L,B,T", [(512, 8, 2048, 3, 256, 32), (768, 12, 3072, 2, 256, 128)])
+def test_layernorm_free_inference_stack(api, d, H, ff, L, B, T):
+    """Inference-only encoder stacks run WITHOUT LayerNorm kernels (hostapi.common.run_encoder_folded: statistics from the
+    producing GEMM's epilogue, gamma folded into the consuming weights, LN-as-residual recomputed in the epilogue): same
+    result as the layer-by-layer path within bf16 round-off, and both within the bf16 bar of the fp32 torch encoder."""
+    from tvt_b200 import ops
+    from tvt_b200.hostapi import common
+    torch.manual_seed(1130)
+    enc = common.make_encoder(d, H, ff, 0.0, L).to(DEV).eval()
+    with torch.no_grad():                      # non-trivial LayerNorm affine parameters and distinct layers
+        for i, layer in enumerate(enc.layers):
+            for nrm in (layer.norm1, layer.norm2):
+                nrm.weight.add_(0.2 * torch.randn_like(nrm.weight))
+                nrm.bias.add_(0.1 * torch.randn_like(nrm.bias))
+            layer.linear1.weight.mul_(1.0 + 0.05 * i)
+    S = T + 1
+    n = B * S
+    assert all(ops.ln_fold_supported(n, N_, K_) for N_, K_ in ((3 * d, d), (d, d), (ff, d), (d, ff)))
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(S, B, d, generator=gen).to(DEV)
+    tok = x.transpose(0, 1).reshape(n, d).to(torch.bfloat16).contiguous()
+    mode = ops.Mode("bf16")
+    import tvt_b200
+    with torch.no_grad():
+        want = enc(x).transpose(0, 1).reshape(n, d)
+        for flag in (True, False):             # first use converts the weights (cached afterwards): keep it out of the launch counts
+            common.FOLD_LAYERNORM = flag
+            common.run_encoder(mode, enc, tok, B, False)
+        l0 = tvt_b200.capi.launches
+        common.FOLD_LAYERNORM = True
+        folded = common.run_encoder(mode, enc, tok, B, False)
+        l1 = tvt_b200.capi.launches
+        common.FOLD_LAYERNORM = False
+        plain = common.run_encoder(mode, enc, tok, B, False)
+        l2 = tvt_b200.capi.launches
+        common.FOLD_LAYERNORM = True
+    assert (l1 - l0) == 5 * L + 1 and (l2 - l1) == 7 * L            # 2 L LayerNorm launches became 1
+    assert_close(folded, plain, 1e-2, "folded vs layer-by-layer")
+    assert_close(plain, want, 2e-2, "layer-by-layer vs torch fp32")
+    assert_close(folded, want, 2e-2, "folded vs torch fp32")
+    # with autograd recording, the stack must take the differentiable path
+    out = common.run_encoder(mode, enc, tok.clone().requires_grad_(True), B, False)
+    assert out.requires_grad
