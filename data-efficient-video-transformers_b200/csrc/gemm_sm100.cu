@@ -44,7 +44,7 @@ struct Params {
   void* out_preact; int preact_f32; long long ld_preact;
   // LayerNorm folded into the epilogue (see tvt_gemm_args): raw (sum, sum of squares) rows, 1 / ln_dim, eps
   const float* ln_in_stats; const float* ln_in_c; const float* ln_res_stats; const float* ln_res_gamma; const float* ln_res_beta;
-  float* stats_out; float ln_inv_d, ln_eps;
+  float* stats_out; float ln_inv_d, ln_eps; int ln_slots;   // partial (sum, sum of squares) slots per row: 2 per 256-column block of the producer
   float* out_f32; long long ld_f32; int atomic_out;
   __nv_bfloat16* out_bf16; __nv_bfloat16* out_bf16_lo; long long ld_bf16;
   unsigned mn_lbo, mn_sbo;  // MN-major descriptor strides (bring-up knob, see tvt_debug_set_mn_desc)
@@ -333,16 +333,15 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, float scale, uint
       }
     }
   }
+  if constexpr (has_stage(kEpi, kStStats)) {   // row statistics from the fp32 values (the bf16 rounding of the stored row is zero-mean noise)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-  if constexpr (has_stage(kEpi, kStStats)) {   // statistics of the STORED (bf16-rounded) row: what the next LayerNorm would read
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float a = __uint_as_float(out[i] << 16), b = __uint_as_float(out[i] & 0xFFFF0000u);
-      ln.sum += a + b;
-      ln.sq = fmaf(a, a, fmaf(b, b, ln.sq));
+    for (int i = 0; i < 32; i += 2) {
+      ln.sum += v[i] + v[i + 1];
+      ln.sq = fmaf(v[i], v[i], fmaf(v[i + 1], v[i + 1], ln.sq));
     }
   }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
 }
 
 template <int kEpi>
@@ -636,7 +635,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (row < p.M) {
-            const float2 st = __ldg(reinterpret_cast<const float2*>((has_stage(kEpi, kStLnIn) ? p.ln_in_stats : p.ln_res_stats) + 2 * row));
+            // the producer's column-block partials, summed in a fixed order (deterministic; no atomics, no zero-fill)
+            const float2* sp = reinterpret_cast<const float2*>(has_stage(kEpi, kStLnIn) ? p.ln_in_stats : p.ln_res_stats) + row * p.ln_slots;
+            float2 st = __ldg(sp);
+            for (int k = 1; k < p.ln_slots; ++k) { const float2 t = __ldg(sp + k); st.x += t.x; st.y += t.y; }
             const float mean = st.x * p.ln_inv_d;
             const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, st.y * p.ln_inv_d), 0.0f) + p.ln_eps);
             if constexpr (has_stage(kEpi, kStLnIn)) { ln.rs = rstd; ln.rb = -mean * rstd; }
@@ -701,10 +703,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         if constexpr (has_stage(kEpi, kStStats)) {
-          if (row_ok) {
-            atomicAdd(p.stats_out + 2 * row, ln.sum);
-            atomicAdd(p.stats_out + 2 * row + 1, ln.sq);
-          }
+          if (row_ok)   // this warp's half of this column block: its own slot of the row (written exactly once)
+            *reinterpret_cast<float2*>(p.stats_out + 2 * (row * (2 * num_n) + 2 * n_blk + half)) = make_float2(ln.sum, ln.sq);
         }
         sphase ^= 1;
         __syncwarp();   // every lane is done with the bias slab before the next tile overwrites it
@@ -999,6 +999,7 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   p.ln_in_stats = a->ln_in_stats; p.ln_in_c = a->ln_in_c; p.ln_res_stats = a->ln_res_stats;
   p.ln_res_gamma = a->ln_res_gamma; p.ln_res_beta = a->ln_res_beta; p.stats_out = a->stats_out;
   p.ln_inv_d = a->ln_dim > 0 ? 1.0f / static_cast<float>(a->ln_dim) : 0.0f; p.ln_eps = a->ln_eps;
+  p.ln_slots = a->ln_dim > 0 ? 2 * static_cast<int>((a->ln_dim + 255) / 256) : 0;
   p.out_bf16 = (__nv_bfloat16*)a->out_bf16; p.out_bf16_lo = (__nv_bfloat16*)a->out_bf16_lo; p.ld_bf16 = a->ld_bf16;
 
   p.mn_lbo = gemm::g_mn_lbo; p.mn_sbo = gemm::g_mn_sbo; p.dbg = gemm::g_dbg;
@@ -1051,6 +1052,7 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     TVT_REQUIRE((!a->ln_in_stats && !a->ln_res_stats) || (a->ln_dim > 0 && a->ln_eps > 0.0f), "tvt_gemm: ln_dim / ln_eps missing");
     TVT_REQUIRE(!(a->ln_in_stats && (a->residual || a->stats_out)), "tvt_gemm: ln_in supports bias (+ relu) only");
     TVT_REQUIRE(!a->stats_out || a->residual, "tvt_gemm: stats_out is implemented for the residual-adding GEMMs");
+    TVT_REQUIRE(!a->stats_out || (reinterpret_cast<uintptr_t>(a->stats_out) & 7) == 0, "tvt_gemm: stats_out must be 8-byte aligned");
     TVT_REQUIRE(al16(a->ln_in_c) && al16(a->ln_res_gamma) && al16(a->ln_res_beta) && (reinterpret_cast<uintptr_t>(a->ln_in_stats) & 7) == 0 &&
                     (reinterpret_cast<uintptr_t>(a->ln_res_stats) & 7) == 0 && a->n % 4 == 0,
                 "tvt_gemm: LayerNorm vectors must be 16-byte aligned, statistics 8-byte aligned");

@@ -69,7 +69,8 @@ def run_encoder_folded(mode, enc, tokens, batch, attn_impl=0):
     import math
     n, d = tokens.shape
     L = len(enc.layers)
-    stats = torch.zeros(2 * L, n, 2, dtype=torch.float32, device=tokens.device)     # (sum, sum of squares) rows of y1 / y2 per layer
+    slots = 2 * ((d + 255) // 256)     # partial (sum, sum of squares) per half of every 256-column block of the producing GEMM
+    stats = torch.empty(2 * L, n, slots, 2, dtype=torch.float32, device=tokens.device)   # rows of y1 / y2 per layer (every slot is written)
     x_real = tokens                # layer input: a materialised tensor (layer 0) ...
     prev = None                    # ... or (y2, stats2, norm2) of the previous layer
     for li, layer in enumerate(enc.layers):

@@ -122,13 +122,15 @@ typedef struct {
    * A post-norm layer's LN(y) = (y - mean) * rstd * gamma + beta feeds a Linear:  LN(y) W^T + b =
    *     rstd_m * (y (W diag(gamma))^T)[m, n]  -  rstd_m * mean_m * c_n  +  b'_n,   c = rowsum(W diag(gamma)),  b' = b + W beta,
    * so the consumer GEMM runs on the PRE-norm tensor y with B = W diag(gamma) (caller-prepared), `bias` = b', and
-   *   ln_in_stats [M, 2] fp32 (sum, sum of squares of y's row over ln_dim columns) + ln_in_c [N]:
+   *   ln_in_stats [M, slots, 2] fp32 (partial sums and sums of squares of y's row, slots = 2 * ceil(ln_dim / 256): one per half of
+   *   every 256-column block of the GEMM that wrote y, summed in slot order by the consumer) + ln_in_c [N]:
    *       v = rstd_m * alpha * acc + (-mean_m rstd_m) * c_n + bias_n           (replaces v = alpha * acc + bias)
    * and LN(y) as the RESIDUAL of the next GEMM is recomputed in its epilogue from the same y:
-   *   residual = y (pre-norm, bf16), ln_res_stats [M, 2], ln_res_gamma / ln_res_beta [N]:
+   *   residual = y (pre-norm, bf16), ln_res_stats [M, slots, 2], ln_res_gamma / ln_res_beta [N]:
    *       v += ((residual - mean_m) * rstd_m) * gamma_n + beta_n               (replaces v += residual)
    * The row statistics are produced by the epilogue of the GEMM that writes y:
-   *   stats_out [M, 2] fp32, caller zero-filled: (sum, sum of squares) of the final output row, atomically accumulated.
+   *   stats_out [M, 2 * ceil(N / 256), 2] fp32: every epilogue warp stores the (sum, sum of squares) of its 128 columns of the
+   *   row (fp32, before the bf16 rounding of the stored value) in its own slot - no atomics, no zero-fill, bit-reproducible.
    * bf16 fast path only (plain bf16 output, both operands K-major, n % 32 == 0); ln_dim = the normalised width, ln_eps. */
   const float* ln_in_stats;
   const float* ln_in_c;

@@ -483,7 +483,10 @@ def test_full_size_properties(api):
     close = lambda u, v: torch.allclose(u, v, rtol=0, atol=2e-3)
     assert torch.equal(a, b) and close(pa, pb)                             # deterministic
     assert torch.equal(c, a[perm]) and close(pc, pa[perm])                 # clip independence
-    assert torch.equal(d_, a) and close(pd_, pa)                           # dropout-free train == eval
+    # dropout-free train == eval up to bf16 round-off: evaluation under no_grad takes the LayerNorm-free stack
+    # (hostapi.common.run_encoder_folded), train mode the layer-by-layer path - two arithmetic routes to the same numbers
+    assert_close(d_, a, 2e-2, "train (no dropout) vs eval logits")
+    assert torch.allclose(pd_, pa, rtol=0, atol=1e-2)
     assert torch.isfinite(a).all() and float(pa.min()) >= 0.0 and float(pa.max()) <= 1.0
 
 
