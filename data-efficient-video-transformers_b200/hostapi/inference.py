@@ -125,7 +125,7 @@ class GraphedForward:
         key = []
         for mode in modes.values():
             for pid, ent in mode._wcache.items():
-                key.append((pid, ent[2].data_ptr(), ent[3].data_ptr() if ent[3] is not None else 0))
+                key.append((str(pid), ent[2].data_ptr(), ent[3].data_ptr() if ent[3] is not None else 0))
         return tuple(sorted(key))
 
     def _stale(self):
@@ -138,12 +138,8 @@ class GraphedForward:
         if len(now) != len(self._key) or any(a[0] != b[0] or a[2] != b[2] for a, b in zip(now, self._key)):
             return True                      # a parameter moved (biases, LayerNorm and head weights are read in place)
         modes = {id(m.mode): m.mode for m in self.module.modules() if isinstance(getattr(m, "mode", None), ops.Mode)}
-        params = {id(p): p for p in self.module.parameters()}
-        for mode in modes.values():
-            for pid, ent in mode._wcache.items():
-                p = params.get(pid)
-                if p is not None and (ent[0]() is not p or ent[1] != p._version):
-                    return True
+        if any(mode.any_stale() for mode in modes.values()):
+            return True
         if self._planes != self._plane_key():
             return True
         self._key = self._weights_key()

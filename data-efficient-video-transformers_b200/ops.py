@@ -238,9 +238,25 @@ class Mode:
                 wp = (wf * g[None, :]).to(torch.bfloat16).contiguous()
                 c = wp.float().sum(dim=1).contiguous()
                 bp = (b.detach().float() + wf @ bt).contiguous()
-            ent = (weakref.ref(w), vers, wp, c, bp)
+            ent = (weakref.ref(w), vers, wp, c, bp, (weakref.ref(b), weakref.ref(gamma), weakref.ref(beta)))
             self._wcache[key] = ent
         return ent[2], ent[3], ent[4]
+
+    def any_stale(self):
+        """True when a cached operand (bf16 planes, three-plane layout, LayerNorm-folded weight) no longer matches the version
+        of the tensors it was derived from - i.e. the next call would rebuild it at a NEW address.  CUDA graphs that captured the
+        old addresses must be re-captured (hostapi.GraphedForward)."""
+        for key, ent in self._wcache.items():
+            w = ent[0]()
+            if w is None:
+                continue
+            if isinstance(key, tuple) and key[1] == "lnfold":
+                srcs = [r() for r in ent[5]]
+                if any(t is None for t in srcs) or ent[1] != (w._version, srcs[0]._version, srcs[1]._version, srcs[2]._version, id(srcs[1])):
+                    return True
+            elif ent[1] != w._version:
+                return True
+        return False
 
     def weight(self, w, rows=None):
         """fp32 master weight [N, K] -> cached (hi, lo) bf16 planes, refreshed when the parameter changes

@@ -158,6 +158,28 @@ def test_shared_parameters_complete_only_after_their_last_contribution(api, prec
         assert_close(grads[True][n], grads[False][n], 1e-5, "shared direct " + n)      # fp32 atomics: summation order varies
 
 
+def test_graphed_folded_inference_recaptures_after_a_weight_update(api):
+    """Same as below at a size whose evaluation forward takes the LayerNorm-free stack: the graph reads the CACHED folded
+    weights (W diag(gamma), c, b'), which a weight OR LayerNorm-parameter update invalidates."""
+    from tvt_b200 import ops
+    kw = dict(in_dims=(256,), d=512, nhead=8, nhid=2048, nlayers=2, dropout=0.0, batch_size=256, frames=32, n_classes=15, fusion="sum")
+    torch.manual_seed(1130)
+    mod = api.FusionTransformer(precision="bf16", **kw).to(DEV).eval()
+    assert ops.ln_fold_supported(256 * 33, 512, 512)
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(256, 32, 256, generator=gen).to(DEV)
+    graphed = api.GraphedForward(lambda t: mod([t])[0], [x], module=mod)
+    before = graphed(x).clone()
+    assert graphed.captures == 1
+    with torch.no_grad():
+        mod.streams[0].transformer_encoder.layers[0].norm1.weight.mul_(1.5)      # only a LayerNorm gamma changes
+        eager = mod([x])[0].clone()
+    got = graphed(x)
+    torch.cuda.synchronize()
+    assert graphed.captures == 2
+    assert torch.equal(got, eager) and not torch.equal(got, before)
+
+
 def test_graphed_forward_recaptures_after_a_weight_update(api):
     """the captured graph holds raw addresses of the cached bf16 weight planes; a plain torch optimizer step
     (what the reference's configure_optimizers returns) re-splits the weights into NEW planes, so the replay must notice
