@@ -16,6 +16,7 @@
 // as bf16 into swizzled shared memory and consumed by the next MMA.  Rows / columns beyond the sequence
 // are masked (the sequences here are 2^k + 1 tokens long: 17, 33, 65, 129).
 #include <cuda.h>
+#include <cstdlib>
 
 #include <mutex>
 #include <type_traits>
@@ -44,6 +45,7 @@ struct Params {
   // backward
   const __nv_bfloat16* o_in; const __nv_bfloat16* do_in; long long lddo;
   __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv; long long lddq, lddk, lddv;
+  int use_tu;                 // fwd_small: tail-key / tail-row score vectors from two N = 16 MMAs instead of CUDA-core dot products
   int prefetch_stride;        // bwd3: CTA bh prefetches the operands of CTA bh + prefetch_stride into L2 (= resident CTAs of the grid)
 };
 
@@ -343,7 +345,9 @@ __global__ void __launch_bounds__(kThreadsFwd) fwd_kernel(const __grid_constant_
 constexpr int kSmallTailKeys = 2;   // per-thread tail keys are unrolled: keep the kernel small (S = 2^k + 1 needs 1)
 
 __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                                                                   const __grid_constant__ CUtensorMap tmV, const Params p) {
+                                                                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK128,
+                                                                   const __grid_constant__ CUtensorMap tmK8, const __grid_constant__ CUtensorMap tmQ8,
+                                                                   const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                       // later: P block 0 (keys 0..63)
@@ -354,6 +358,8 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
   uint64_t* bar_q = bars + 1;
   uint64_t* bar_s = bars + 2;
   uint64_t* bar_o = bars + 3;
+  uint64_t* bar_t = bars + 4;     // tail-score MMAs done (see below)
+  uint64_t* bar_tu = bars + 6;    // ... and read out of TMEM by the four worker warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* tail_q = reinterpret_cast<float*>(bars + 8);   // [8 + 4 * 64] reduction scratch of the tail-row path
   float* tail_p = tail_q + 8 + 4 * HD;                  // [KC] probabilities of the current tail row
@@ -367,6 +373,12 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
   const int tk = p.Sk - n_keys;                    // tail keys (per thread)
   const int n_mma = (n_keys + 15) & ~15;
   const float sl2 = p.scale * kLog2e;
+  // The "+1" of S = 2^k + 1: the tail key's score column (q_i . k_128 for every main row i) and the tail query row's score row
+  // (k_j . q_128 for every main key j) are dot products over head_dim that cost a quarter of this kernel's instructions on CUDA
+  // cores.  With use_tu the tensor cores produce both from ONE 16-row B block = { K rows 128..135 | Q rows 128..135 } (rows 128..143
+  // of the K tile): U = Q_main B^T (columns 0..7 = tail keys) and T = K_main B^T (columns 8..15 = tail query rows), two N = 16
+  // MMAs issued ahead of the main S tile into TMEM columns [0, 32), read into registers by the workers, then overwritten by S.
+  const bool tu = p.use_tu != 0;
   // 32-bit shared-space addresses of the tiles: the CUDA-core paths below read them with ld.shared (a generic-pointer
   // dereference costs 64-bit address arithmetic per load, which was a fifth of this kernel's instructions)
   const uint32_t sQ_s = smem_u32(sQ), sK_s = smem_u32(sK), sV_s = smem_u32(sV), tail_p_s = smem_u32(tail_p);
@@ -376,6 +388,8 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     mbar_init(smem_u32(bar_q), 1);
     mbar_init(smem_u32(bar_s), 1);
     mbar_init(smem_u32(bar_o), 1);
+    mbar_init(smem_u32(bar_t), 1);
+    mbar_init(smem_u32(bar_tu), 4);
     fence_mbar_init();
   }
   if (warp == 4) {
@@ -391,18 +405,57 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
   pdl_trigger();
 
   if (issuer) {
-    mbar_arrive_expect_tx(smem_u32(bar_kv), 2 * p.sk_pad * 128);
-    for (int r = 0; r < p.sk_pad; r += p.kv_box) {
-      tma_load_2d(smem_u32(sK + r * 128), &tmK, smem_u32(bar_kv), h * HD, b * p.Sk + r);
-      tma_load_2d(smem_u32(sV + r * 128), &tmV, smem_u32(bar_kv), h * HD, b * p.Sk + r);
+    if (tu) {   // K rows 0..135 (main + tail keys), Q tail rows into rows 136..143 of the K tile, V as usual
+      mbar_arrive_expect_tx(smem_u32(bar_kv), (136 + p.sk_pad) * 128);
+      tma_load_2d(smem_u32(sK), &tmK128, smem_u32(bar_kv), h * HD, b * p.Sk);
+      tma_load_2d(smem_u32(sK + 128 * 128), &tmK8, smem_u32(bar_kv), h * HD, b * p.Sk + 128);
+      for (int r = 0; r < p.sk_pad; r += p.kv_box) tma_load_2d(smem_u32(sV + r * 128), &tmV, smem_u32(bar_kv), h * HD, b * p.Sk + r);
+      mbar_arrive_expect_tx(smem_u32(bar_q), (128 + 8) * 128);
+      tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq);
+      tma_load_2d(smem_u32(sK + 136 * 128), &tmQ8, smem_u32(bar_q), h * HD, b * p.Sq + 128);
+    } else {
+      mbar_arrive_expect_tx(smem_u32(bar_kv), 2 * p.sk_pad * 128);
+      for (int r = 0; r < p.sk_pad; r += p.kv_box) {
+        tma_load_2d(smem_u32(sK + r * 128), &tmK, smem_u32(bar_kv), h * HD, b * p.Sk + r);
+        tma_load_2d(smem_u32(sV + r * 128), &tmV, smem_u32(bar_kv), h * HD, b * p.Sk + r);
+      }
+      mbar_arrive_expect_tx(smem_u32(bar_q), 128 * 128);
+      tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq);
     }
-    mbar_arrive_expect_tx(smem_u32(bar_q), 128 * 128);
-    tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq);
     mbar_wait(smem_u32(bar_kv), 0);
     mbar_wait(smem_u32(bar_q), 0);
     tc_fence_after();
+    if (tu) {
+      mma_kk(tmem_base, smem_u32(sQ), smem_u32(sK + 128 * 128), 16);        // U: columns [0, 16)
+      mma_kk(tmem_base + 16, smem_u32(sK), smem_u32(sK + 128 * 128), 16);   // T: columns [16, 32)
+      tc_commit(smem_u32(bar_t));
+      mbar_wait(smem_u32(bar_tu), 0);                                       // the workers hold U / T in registers
+      tc_fence_after();
+    }
     mma_kk(tmem_base, smem_u32(sQ), smem_u32(sK), n_mma);      // S = Q K^T over the main keys
     tc_commit(smem_u32(bar_s));
+  }
+
+  // tail scores from the tensor cores: this thread's row of U (tail keys) and of T (tail query rows)
+  float u_tail[kSmallTailKeys], t_tail[kMaxTail];
+#pragma unroll
+  for (int t = 0; t < kSmallTailKeys; ++t) u_tail[t] = 0.0f;
+#pragma unroll
+  for (int t = 0; t < kMaxTail; ++t) t_tail[t] = 0.0f;
+  if (tu && warp < 4) {
+    mbar_wait(smem_u32(bar_t), 0);
+    tc_fence_after();
+    uint32_t ru[16], rt[16];
+    tmem_ld_32x32b_x16(tmem_base + lane_addr, ru);
+    tmem_ld_32x32b_x16(tmem_base + lane_addr + 16, rt);
+    tmem_ld_wait_dep(ru, rt);
+#pragma unroll
+    for (int t = 0; t < kSmallTailKeys; ++t) u_tail[t] = __uint_as_float(ru[t]);
+#pragma unroll
+    for (int t = 0; t < kMaxTail; ++t) t_tail[t] = __uint_as_float(rt[8 + t]);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(bar_tu));
   }
 
   if (warp < 4 && tq_rows > 0) {
@@ -414,7 +467,8 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     float* part = tail_q + 8;            // [4][64] P V partials of the four warps
     // the tail query row comes straight from global memory: fetch it before waiting for the K / V tiles
     uint4 qraw[8];
-    {
+    const bool need_q = !tu || tid < tk;       // with U / T only the tail-key x tail-row corner is still a CUDA-core dot product
+    if (need_q) {
       const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + n_rows) * p.ldq + h * HD;
 #pragma unroll
       for (int c = 0; c < 8; ++c) qraw[c] = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
@@ -422,12 +476,27 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
     mbar_wait(smem_u32(bar_kv), 0);
     for (int t = 0; t < tq_rows; ++t) {
       const int row = n_rows + t;
-      if (t > 0) {
+      if (t > 0 && need_q) {
         const __nv_bfloat16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + row) * p.ldq + h * HD;
 #pragma unroll
         for (int c = 0; c < 8; ++c) qraw[c] = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
       }
       float s0 = 0.0f, s1 = 0.0f;
+      if (tu) {
+        s0 = t_tail[0];
+#pragma unroll
+        for (int i = 1; i < kMaxTail; ++i) s0 = t == i ? t_tail[i] : s0;
+        if (tid < tk) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float qf[8], kf[8];
+            Vec16<__nv_bfloat16>::unpack(qraw[c], qf);
+            Vec16<__nv_bfloat16>::unpack(lds128(sK_s + sw128(128 + tid, c)), kf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s1 += qf[i] * kf[i];
+          }
+        }
+      } else
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float qf[8], kf[8];
@@ -500,13 +569,17 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
       st[t] = -INFINITY;
       if (t < tk) {
         float acc = 0.0f;
+        if (tu) {
+          acc = u_tail[t];
+        } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float qf[8], kf[8];
-          Vec16<__nv_bfloat16>::unpack(lds128(sQ_s + sw128(tid, c)), qf);
-          Vec16<__nv_bfloat16>::unpack(lds128(sK_s + sw128(128 + t, c)), kf);
+          for (int c = 0; c < 8; ++c) {
+            float qf[8], kf[8];
+            Vec16<__nv_bfloat16>::unpack(lds128(sQ_s + sw128(tid, c)), qf);
+            Vec16<__nv_bfloat16>::unpack(lds128(sK_s + sw128(128 + t, c)), kf);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc += qf[i] * kf[i];
+            for (int i = 0; i < 8; ++i) acc += qf[i] * kf[i];
+          }
         }
         st[t] = acc;
         mx = fmaxf(mx, acc);
@@ -1680,7 +1753,15 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
   if (p.Sq <= 128 + kMaxTail && p.Sk <= 128 + kSmallTailKeys) {
     const size_t bytes_s = 1024 + 16384 + 2 * (size_t)KC * 128 + 64 + (8 + 4 * HD + KC) * 4;   // 55 KB: 4 CTAs / SM
     if ((rc = set_smem(fwd_small_kernel, bytes_s, "tvt_attention_fwd")) != TVT_OK) return rc;
-    if (launch_pdl(fwd_small_kernel, p.B * p.H, kThreads, bytes_s, s, 1, tq, tk, tv, p) != cudaSuccess) return check_launch("tvt_attention_fwd");
+    CUtensorMap tk128 = tk, tk8 = tk, tq8 = tq;
+    static const int tu_enabled = [] { const char* e = getenv("TVT_ATTN_TU"); return e ? atoi(e) : 1; }();
+    p.use_tu = tu_enabled && (p.Sq > 128 || p.Sk > 128) && p.Sq >= 128 && p.Sk >= 128;
+    if (p.use_tu) {
+      if ((rc = make_map(&tk128, a->k, a->batch * a->sk, w, a->ldk, 128)) != TVT_OK) return rc;
+      if ((rc = make_map(&tk8, a->k, a->batch * a->sk, w, a->ldk, 8)) != TVT_OK) return rc;
+      if ((rc = make_map(&tq8, a->q, a->batch * a->sq, w, a->ldq, 8)) != TVT_OK) return rc;
+    }
+    if (launch_pdl(fwd_small_kernel, p.B * p.H, kThreads, bytes_s, s, 1, tq, tk, tv, tk128, tk8, tq8, p) != cudaSuccess) return check_launch("tvt_attention_fwd");
     return check_launch("tvt_attention_fwd");
   }
   const int kv = ((p.sk_pad * 128) + 1023) & ~1023;
