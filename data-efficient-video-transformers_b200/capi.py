@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
                 ("preact_dtype", i32), ("ld_preact", i64), ("out_f32", vp), ("ld_f32", i64), ("atomic_out", i32),
                 ("out_bf16", vp), ("out_bf16_lo", vp), ("ld_bf16", i64),
                 ("ln_in_stats", vp), ("ln_in_c", vp), ("ln_res_stats", vp), ("ln_res_gamma", vp), ("ln_res_beta", vp),
-                ("stats_out", vp), ("ln_dim", i64), ("ln_eps", f32), ("reserved", i32)]
+                ("stats_out", vp), ("ln_dim", i64), ("ln_eps", f32), ("reserved", i32), ("a_rowsum", vp)]
 
 
 class LayerNormFwdArgs(C.Structure):
@@ -196,7 +196,7 @@ ENTRY_POINTS = {
     "tvt_feature_augment": FeatureAugmentArgs,
 }
 PLAIN_SYMBOLS = ("tvt_last_error", "tvt_version", "tvt_device_check", "tvt_set_seed_source", "tvt_step_counter_advance",
-                 "tvt_gemm_ln_fold_supported")
+                 "tvt_gemm_ln_fold_supported", "tvt_gemm_rowsum_supported")
 
 _lib = None
 launches = 0  # number of kernel-launching entry-point calls made through this module (bench.py reads it)
@@ -221,6 +221,8 @@ def load():
     lib.tvt_step_counter_advance.argtypes = [vp, C.c_int, vp]
     lib.tvt_gemm_ln_fold_supported.restype = C.c_int
     lib.tvt_gemm_ln_fold_supported.argtypes = [i64, i64, i64]
+    lib.tvt_gemm_rowsum_supported.restype = C.c_int
+    lib.tvt_gemm_rowsum_supported.argtypes = [i64, i64, i64, i32]
     for name, st in ENTRY_POINTS.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

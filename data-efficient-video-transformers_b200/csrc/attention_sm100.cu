@@ -46,7 +46,7 @@ struct Params {
   const __nv_bfloat16* o_in; const __nv_bfloat16* do_in; long long lddo;
   __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv; long long lddq, lddk, lddv;
   int use_tu;                 // fwd_small: tail-key / tail-row score vectors from two N = 16 MMAs instead of CUDA-core dot products
-  int prefetch_stride;        // bwd3: CTA bh prefetches the operands of CTA bh + prefetch_stride into L2 (= resident CTAs of the grid)
+  int prefetch_stride;        // fwd_small / bwd3: CTA bh prefetches the operands of CTA bh + prefetch_stride into L2 (= resident CTAs of the grid)
 };
 
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a [rows x 128 B] swizzled tile.
@@ -421,6 +421,16 @@ __global__ void __launch_bounds__(kThreads, 4) fwd_small_kernel(const __grid_con
       }
       mbar_arrive_expect_tx(smem_u32(bar_q), 128 * 128);
       tma_load_2d(smem_u32(sQ), &tmQ, smem_u32(bar_q), h * HD, b * p.Sq);
+    }
+    // pull the tiles of the CTA that will take this one's place on the SM into L2 (the kernel is a latency chain: the
+    // successor's TMA loads then complete at L2 rather than DRAM latency)
+    const int nb = bh + p.prefetch_stride;
+    if (p.prefetch_stride > 0 && nb < static_cast<int>(gridDim.x)) {
+      const int b2 = nb / p.H, h2 = nb % p.H;
+      if (tu) tma_prefetch_2d(&tmK128, h2 * HD, b2 * p.Sk);
+      else for (int r = 0; r < p.sk_pad; r += p.kv_box) tma_prefetch_2d(&tmK, h2 * HD, b2 * p.Sk + r);
+      for (int r = 0; r < p.sk_pad; r += p.kv_box) tma_prefetch_2d(&tmV, h2 * HD, b2 * p.Sk + r);
+      tma_prefetch_2d(&tmQ, h2 * HD, b2 * p.Sq);
     }
     mbar_wait(smem_u32(bar_kv), 0);
     mbar_wait(smem_u32(bar_q), 0);
@@ -1756,6 +1766,8 @@ int launch_fwd(const tvt_attention_fwd_args* a, cudaStream_t s) {
     CUtensorMap tk128 = tk, tk8 = tk, tq8 = tq;
     static const int tu_enabled = [] { const char* e = getenv("TVT_ATTN_TU"); return e ? atoi(e) : 1; }();
     p.use_tu = tu_enabled && (p.Sq > 128 || p.Sk > 128) && p.Sq >= 128 && p.Sk >= 128;
+    static const int pf_enabled = [] { const char* e = getenv("TVT_ATTN_FWD_PREFETCH"); return e ? atoi(e) : 1; }();
+    p.prefetch_stride = pf_enabled ? 4 * num_sms() : 0;   // four resident CTAs per SM
     if (p.use_tu) {
       if ((rc = make_map(&tk128, a->k, a->batch * a->sk, w, a->ldk, 128)) != TVT_OK) return rc;
       if ((rc = make_map(&tk8, a->k, a->batch * a->sk, w, a->ldk, 8)) != TVT_OK) return rc;

@@ -46,6 +46,7 @@ struct Params {
   const float* ln_in_stats; const float* ln_in_c; const float* ln_res_stats; const float* ln_res_gamma; const float* ln_res_beta;
   float* stats_out; float ln_inv_d, ln_eps; int ln_slots;   // partial (sum, sum of squares) slots per row: 2 per 256-column block of the producer
   float* out_f32; long long ld_f32; int atomic_out;
+  float* a_rowsum;          // kEpiAtomicSum: [M] += sum over k of A[m, k]
   __nv_bfloat16* out_bf16; __nv_bfloat16* out_bf16_lo; long long ld_bf16;
   unsigned mn_lbo, mn_sbo;  // MN-major descriptor strides (bring-up knob, see tvt_debug_set_mn_desc)
   int dbg;                  // bring-up knob: low 2 bits 1 = epilogue drains TMEM only, 2 = no global stores; 4 = no main loop; 8 = no epilogue
@@ -56,7 +57,7 @@ static int g_dbg = 0;
 static int g_pair = [] { const char* e = getenv("TVT_GEMM_PAIR"); return e ? atoi(e) : 1; }();   // bring-up knob: 0 = never use the CTA-pair kernels
 static long long g_fast_fallbacks = 0;   // fast-path launches that had no exact-stage kernel (see tvt_gemm)
 
-template <int BN, int kPlanes, bool kSide, bool kFastEpi, bool kCta2 = false, int kSlabs = 1>
+template <int BN, int kPlanes, bool kSide, bool kFastEpi, bool kCta2 = false, int kSlabs = 1, bool kRowsum = false>
 struct Cfg {
   static constexpr int kAPlane = BM * BK * 2;
   static constexpr int kBRows = kCta2 ? BN / 2 : BN;   // a CTA pair splits the B tile between its two CTAs
@@ -67,8 +68,12 @@ struct Cfg {
   static constexpr int kSideSlots = BN / 128;  // one per two 32-column chunk steps of the epilogue warps
   static constexpr int kSideBytes = kSide ? kSideSlots * kSideSlotBytes : 0;
   static constexpr int kStages = (kSmemLimit - 2048 - kEpiBytes - kSideBytes) / kStageBytes;
-  static constexpr int kAccStages = 2;
-  static constexpr int kTmemCols = kAccStages * BN;  // 512 or 256: powers of two
+  // kRowsum (kEpiAtomicSum): 16 extra accumulator columns per stage hold A . 1 (the bias gradient of a wgrad GEMM); a 256-wide
+  // tile then keeps ONE accumulator stage (512 TMEM columns in all) - the wgrad tiles it serves run hundreds of k-blocks per
+  // epilogue, so the lost overlap is noise
+  static constexpr int kAccStages = (kRowsum && BN == 256) ? 1 : 2;
+  static constexpr int kSumCol = kAccStages * BN;     // first column of the row-sum accumulators (16 per stage)
+  static constexpr int kTmemCols = kRowsum ? 512 : kAccStages * BN;  // 512 or 256: powers of two
   static constexpr int kSmemBytes = kStages * kStageBytes + kSideBytes + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(!kSide || kPlanes == 2 || kStages >= 3, "side-ring kernels keep three operand stages");
@@ -106,7 +111,10 @@ __device__ __forceinline__ void store8(void* base, int is_f32, long long off, co
 //   kEpiAtomic : split-K fp32 red.add only
 //   kEpiGeneric: every stage (fp32 operands, pre-activation store, gelu, hi/lo planes, fp32 output ...)
 // kEpiFast + a stage mask (kStRelu ...) is a kernel with exactly those stages compiled in, unconditionally.
-enum { kEpiGeneric = 0, kEpiAtomic = 2, kEpiFast = 16 };
+//   kEpiAtomicSum: kEpiAtomic + the row sums of the A operand over the contraction (tvt_gemm_args.a_rowsum): one extra N = 16
+//                MMA per k-step against a constant tile of ones, on every num_n-th k-block of a tile
+enum { kEpiGeneric = 0, kEpiAtomic = 2, kEpiAtomicSum = 3, kEpiFast = 16 };
+__host__ __device__ constexpr bool is_atomic(int kEpi) { return kEpi == kEpiAtomic || kEpi == kEpiAtomicSum; }
 enum { kStRelu = 1, kStMask = 2, kStDrop = 4, kStRes = 8 };
 // LayerNorm-folded inference epilogues (tvt_gemm_args.ln_*): kStLnIn = the A operand is a PRE-norm tensor (per-row rstd / mean
 // and the per-column c vector rebuild LN(y) W^T); kStLnRes = the residual is LN(side operand), recomputed; kStStats = accumulate
@@ -347,7 +355,7 @@ __device__ __forceinline__ void epilogue_fast(const Params& p, float scale, uint
 template <int kEpi>
 __device__ __forceinline__ void epilogue32(const Params& p, long long row, int col0, int ng, float (&v)[32],
                                            const uint32_t (&mask_pk)[16], const uint32_t (&res_pk)[16], bool pre, uint32_t bias_s) {
-  if constexpr (kEpi == kEpiAtomic) epilogue_atomic(p, row, col0, ng, v);
+  if constexpr (is_atomic(kEpi)) epilogue_atomic(p, row, col0, ng, v);
   else epilogue_stages<kEpi>(p, row, col0, ng, v, mask_pk, res_pk, pre, bias_s);
 }
 
@@ -397,7 +405,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
             const __grid_constant__ CUtensorMap tmSide, const Params p) {
   constexpr bool kSide = has_side(kEpi);
-  using C = Cfg<BN, kPlanes, kSide, is_fast(kEpi), kCta2, epi_slabs(kEpi)>;
+  constexpr bool kRowsum = kEpi == kEpiAtomicSum;
+  using C = Cfg<BN, kPlanes, kSide, is_fast(kEpi), kCta2, epi_slabs(kEpi), kRowsum>;
   constexpr int kCtas = kCta2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -435,6 +444,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+  }
+  if constexpr (kRowsum) {   // the B operand of the row-sum MMAs: 16 K-major rows of bf16 ones (8 per CTA of a pair), in the unused epilogue staging
+    static_assert(C::kEpiBytes >= 2048 && kPlanes == 1, "row sums: single-plane kernels, 2 KB of ones");
+    for (int i = threadIdx.x; i < 512; i += kThreads) reinterpret_cast<uint32_t*>(epi_stage)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
   }
   if (warp == kEpiWarps + 1) {
     if constexpr (kCta2) {
@@ -520,6 +534,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         uint32_t accumulate = 0;
+        // the row sums are shared out over the column blocks of a row block: the tile of column block j adds the k-blocks with
+        // kb % num_n == j (an N = 16 MMA costs far more than 1/16 of the N = 256 one, and a launch is as slow as its slowest tile)
+        const int sum_blk = w % num_n;
+        uint32_t acc_sums = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           if (p.dbg & 4) break;
           mbar_wait(smem_u32(&full_bar[stage]), phase);
@@ -541,6 +559,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if constexpr (kCta2) tc_mma_f16_ss_cta2(d_tmem, adesc, bdesc, idesc, accumulate);
               else tc_mma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
               accumulate = 1;
+            }
+          }
+          if constexpr (kRowsum) {
+            if (kb % num_n == sum_blk) {   // [BM x 16] += A . ones^T, after the block's main MMAs (switching shape per k-step stalls the pipe)
+              constexpr uint32_t idesc1 = make_idesc_bf16(BM * kCtas, 16, kAMN, false);
+              const uint32_t sa = smem_u32(st);
+              const uint32_t d_sums = tmem_base + C::kSumCol + as * 16;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t adesc = kAMN ? make_smem_desc_sw128(sa + k * 16 * 128, p.mn_lbo, p.mn_sbo)
+                                            : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                const uint64_t odesc = make_smem_desc_sw128(smem_u32(epi_stage) + k * 32, 16, 1024);
+                if constexpr (kCta2) tc_mma_f16_ss_cta2(d_sums, adesc, odesc, idesc1, acc_sums);
+                else tc_mma_f16_ss(d_sums, adesc, odesc, idesc1, acc_sums);
+                acc_sums = 1;
+              }
             }
           }
           commit(&empty_bar[stage]);
@@ -716,7 +750,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint4 pf[4];
         if (pre_res) fetch_issue(p.residual, p.ld_residual, row0, colbase, p.M, p.N, lane, pf);
         else if (pre_mask) fetch_issue(p.relu_mask, p.ld_mask, row0, colbase, p.M, p.N, lane, pf);
-        if constexpr (kEpi != kEpiAtomic) {
+        if constexpr (!is_atomic(kEpi)) {
           // while the main loop of this tile runs: pull the rest of the residual / mask slab into L2 (the register
           // prefetch is only one chunk deep) and copy this warp's bias columns to shared memory
           if (pre_res || pre_mask) {
@@ -792,6 +826,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
           }
         }
+        if constexpr (kRowsum) {   // this row's sum of A over the split's k range (16 identical columns: take the first)
+          const int kb_first = kb0 + (n_blk - kb0 % num_n + num_n) % num_n;   // this tile's first row-sum k-block
+          if (kb_first < kb1 && half == 0 && !(p.dbg & 8)) {
+            uint32_t r1[16];
+            tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + C::kSumCol + as * 16, r1);
+            tmem_ld_wait_dep(r1);
+            if (row_ok) atomicAdd(p.a_rowsum + row, __uint_as_float(r1[0]));
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -855,7 +898,7 @@ static int make_map(CUtensorMap* m, const void* ptr, long long inner, long long 
 
 template <int BN, bool kAMN, bool kBMN, int kPlanes, int kEpi, bool kCta2 = false>
 static int launch(const tvt_gemm_args* a, const Params& p, cudaStream_t stream) {
-  using C = Cfg<BN, kPlanes, has_side(kEpi), is_fast(kEpi), kCta2, epi_slabs(kEpi)>;
+  using C = Cfg<BN, kPlanes, has_side(kEpi), is_fast(kEpi), kCta2, epi_slabs(kEpi), kEpi == kEpiAtomicSum>;
   CUtensorMap tmA, tmAlo, tmB, tmBlo, tmSide;
   int rc;
   auto mapA = [&](CUtensorMap* m, const void* ptr) {
@@ -939,6 +982,20 @@ extern "C" int tvt_gemm_ln_fold_supported(int64_t m, int64_t n, int64_t k) {
   return (wpair + npair - 1) / npair <= (w256 + nsm - 1) / nsm ? 1 : 0;
 }
 
+// 1 when tvt_gemm would run this split-K / accumulating fp32 GEMM with MN-major operands (the wgrad orientation) on the CTA-pair
+// [256 x 256] tiles, i.e. when tvt_gemm_args.a_rowsum is available for it (the same selection as in tvt_gemm below).
+extern "C" int tvt_gemm_rowsum_supported(int64_t m, int64_t n, int64_t k, int32_t splits) {
+  if (m <= 0 || n <= 0 || k <= 0 || splits < 1 || m % 8 || n % 8 || !tvt::gemm::g_pair) return 0;
+  const long long nsm = tvt::num_sms(), kb = (k + tvt::gemm::BK - 1) / tvt::gemm::BK, kb_per = (kb + splits - 1) / splits;
+  if (splits > kb) return 0;
+  const long long m_tiles = (m + 127) / 128;
+  const long long w256 = m_tiles * ((n + 255) / 256) * splits, w128 = m_tiles * ((n + 127) / 128) * splits;
+  const long long c256 = ((w256 + nsm - 1) / nsm) * (kb_per * 512 + 3000), c128 = ((w128 + nsm - 1) / nsm) * (kb_per * 400 + 1800);
+  if (n <= 128 || c128 < c256) return 0;
+  const long long wpair = ((m + 255) / 256) * ((n + 255) / 256) * splits, npair = nsm / 2;
+  return (wpair + npair - 1) / npair <= (w256 + nsm - 1) / nsm ? 1 : 0;
+}
+
 extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   using namespace tvt;
   TVT_REQUIRE(a != nullptr, "tvt_gemm: null args");
@@ -995,7 +1052,7 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
     for (int r = 0; r < kDropoutRounds; ++r) p.drop_rk[r] = static_cast<unsigned>(a->dropout_seed) + r * kDropoutWeyl;
   }
   p.out_preact = a->out_preact; p.preact_f32 = a->preact_dtype == TVT_F32; p.ld_preact = a->ld_preact;
-  p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32; p.atomic_out = a->atomic_out;
+  p.out_f32 = a->out_f32; p.ld_f32 = a->ld_f32; p.atomic_out = a->atomic_out; p.a_rowsum = a->a_rowsum;
   p.ln_in_stats = a->ln_in_stats; p.ln_in_c = a->ln_in_c; p.ln_res_stats = a->ln_res_stats;
   p.ln_res_gamma = a->ln_res_gamma; p.ln_res_beta = a->ln_res_beta; p.stats_out = a->stats_out;
   p.ln_inv_d = a->ln_dim > 0 ? 1.0f / static_cast<float>(a->ln_dim) : 0.0f; p.ln_eps = a->ln_eps;
@@ -1022,6 +1079,13 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
                     (a->act == TVT_ACT_NONE || a->act == TVT_ACT_RELU) && !(a->residual && a->residual_dtype == TVT_F32) &&
                     !(a->relu_mask && a->mask_dtype == TVT_F32) && !(a->residual && a->relu_mask) && a->n % 32 == 0 &&
                     al32(a->out_bf16, a->ld_bf16);
+  if (a->a_rowsum) {
+    TVT_REQUIRE(a->atomic_out && !a->a_lo && a->a_mn_major && a->b_mn_major && (reinterpret_cast<uintptr_t>(a->a_rowsum) & 3) == 0,
+                "tvt_gemm: a_rowsum needs atomic_out, single bf16 planes and MN-major operands (the wgrad orientation)");
+    TVT_REQUIRE(tvt_gemm_rowsum_supported(a->m, a->n, a->k, a->splits),
+                "tvt_gemm: a_rowsum is built for the CTA-pair [256 x 256] tiles (ask tvt_gemm_rowsum_supported first)");
+    return gemm::launch<256, true, true, 1, gemm::kEpiAtomicSum, true>(a, p, s);
+  }
   if (a->a_lo) {
     if (a->atomic_out) return gemm::dispatch_width<2, gemm::kEpiAtomic>(narrow, a, p, s);
     return gemm::dispatch_width<2, gemm::kEpiGeneric>(narrow, a, p, s);

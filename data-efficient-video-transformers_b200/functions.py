@@ -139,11 +139,12 @@ class EncoderLayerFn(torch.autograd.Function):
         s_l2w, s_l2b = _Sink(P[6], (d, ff), dev), _Sink(P[7], (d,), dev)
         s_n1w, s_n1b, s_n2w, s_n2b = (_Sink(P[i], (d,), dev) for i in (8, 9, 10, 11))
 
-        def wgrad(sink, dyp, xp, M, N, K):
+        def wgrad(sink, dyp, xp, M, N, K, bias_grad=None, dy=None):
+            # bias_grad += colsum(dy): inside the weight-gradient GEMM when its kernel selection allows (ops.Mode.wgrad)
             if sink.direct:
-                m.wgrad(dyp, xp, M, N, K, out=sink.buf, accumulate=True)
+                m.wgrad(dyp, xp, M, N, K, out=sink.buf, accumulate=True, bias_grad=bias_grad, dy=dy)
             else:
-                sink.buf = m.wgrad(dyp, xp, M, N, K)
+                sink.buf = m.wgrad(dyp, xp, M, N, K, bias_grad=bias_grad, dy=dy)
 
         # ---- LN2 and the feed-forward branch
         dy2, dz2 = ops.layernorm_bwd(dout, y2, mean2, rstd2, n2_w, dgamma=s_n2w.zeros(), dbeta=s_n2b.zeros(), dbias=s_l2b.zeros(),
@@ -154,11 +155,9 @@ class EncoderLayerFn(torch.autograd.Function):
         dl2w = s_l2w.result()
         dh = m.dgrad(dz2p, n, d, l2_w, relu_mask=h if cfg.act == ACT_RELU else None,
                      gelu_gate=z if cfg.act == ACT_GELU else None, dropout_p=p, seed=seeds[2])
-        ops.colsum(dh, s_l1b.zeros())
-        dl1b = s_l1b.result()
         dhp = m.split(dh)
-        wgrad(s_l1w, dhp, m.split(x1), n, ff, d)
-        dl1w = s_l1w.result()
+        wgrad(s_l1w, dhp, m.split(x1), n, ff, d, bias_grad=s_l1b.zeros(), dy=dh)
+        dl1w, dl1b = s_l1w.result(), s_l1b.result()
         dx1 = m.dgrad(dhp, n, ff, l1_w, residual=dy2)
         # ---- LN1 and the attention branch
         dy1, dz1 = ops.layernorm_bwd(dx1, y1, mean1, rstd1, n1_w, dgamma=s_n1w.zeros(), dbeta=s_n1b.zeros(), dbias=s_ob.zeros(),
@@ -175,9 +174,8 @@ class EncoderLayerFn(torch.autograd.Function):
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
             ops.attention_bwd(q, k, v, attn, dattn, lse, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H, Sq, Sk,
                               hd, scale, dropout_p=p, seed=seeds[0], impl=cfg.attn_impl)
-            ops.colsum(dqkv, dinb_buf)
             dqkvp = m.split(dqkv)
-            wgrad(s_inw, dqkvp, m.split(x), n, 3 * d, d)
+            wgrad(s_inw, dqkvp, m.split(x), n, 3 * d, d, bias_grad=dinb_buf, dy=dqkv)
             dx = m.dgrad(dqkvp, n, 3 * d, in_w, residual=dy1) if ctx.needs_input_grad[1] else None
             dmem = None
         else:
@@ -186,13 +184,11 @@ class EncoderLayerFn(torch.autograd.Function):
             dkv = torch.empty_like(kv)
             ops.attention_bwd(qkv, kv[:, :d], kv[:, d:], attn, dattn, lse, dq, dkv[:, :d], dkv[:, d:], B, H, Sq, Sk,
                               hd, scale, dropout_p=p, seed=seeds[0], impl=cfg.attn_impl)
-            ops.colsum(dq, dinb_buf[:d])
-            ops.colsum(dkv, dinb_buf[d:])
             dqp, dkvp = m.split(dq), m.split(dkv)
             if not s_inw.direct:
                 s_inw.buf = torch.empty(3 * d, d, dtype=torch.float32, device=dev)
-            m.wgrad(dqp, m.split(x), n, d, d, out=s_inw.buf[:d], accumulate=s_inw.direct)
-            m.wgrad(dkvp, m.split(mem), nk, 2 * d, d, out=s_inw.buf[d:], accumulate=s_inw.direct)
+            m.wgrad(dqp, m.split(x), n, d, d, out=s_inw.buf[:d], accumulate=s_inw.direct, bias_grad=dinb_buf[:d], dy=dq)
+            m.wgrad(dkvp, m.split(mem), nk, 2 * d, d, out=s_inw.buf[d:], accumulate=s_inw.direct, bias_grad=dinb_buf[d:], dy=dkv)
             dx = m.dgrad(dqp, n, d, in_w, residual=dy1, rows=(0, d)) if ctx.needs_input_grad[1] else None
             dmem = m.dgrad(dkvp, nk, 2 * d, in_w, rows=(d, 3 * d)) if ctx.needs_input_grad[2] else None
         dinw, dinb = s_inw.result(), s_inb.result()
@@ -243,14 +239,12 @@ class PreNormLayerFn(torch.autograd.Function):
         # ---- feed-forward branch: out = x1 + Drop(W2 h + b2)
         dz2 = ops.act_bwd(dout, dout, ACT_NONE, p, seeds[2]) if p > 0 else dout
         dl2b = _zeros(d, dev)
-        ops.colsum(dz2, dl2b)
         dz2p = m.split(dz2)
-        dl2w = m.wgrad(dz2p, m.split(h), n, d, ff)
+        dl2w = m.wgrad(dz2p, m.split(h), n, d, ff, bias_grad=dl2b, dy=dz2)
         dzp = m.dgrad(dz2p, n, d, l2_w, gelu_gate=z, dropout_p=p, seed=seeds[1])      # d(pre-GELU)
         dl1b = _zeros(ff, dev)
-        ops.colsum(dzp, dl1b)
         dzpp = m.split(dzp)
-        dl1w = m.wgrad(dzpp, m.split(xn2), n, ff, d)
+        dl1w = m.wgrad(dzpp, m.split(xn2), n, ff, d, bias_grad=dl1b, dy=dzp)
         dxn2 = m.dgrad(dzpp, n, ff, l1_w)
         dn2w, dn2b = _zeros(d, dev), _zeros(d, dev)
         dx1, _ = ops.layernorm_bwd(dxn2, x1, mean2, rstd2, n2_w, dgamma=dn2w, dbeta=dn2b, dres=dout)
@@ -258,9 +252,8 @@ class PreNormLayerFn(torch.autograd.Function):
         if ctx.has_out:
             dz1 = ops.act_bwd(dx1, dx1, ACT_NONE, p, seeds[0]) if p > 0 else dx1
             dob = _zeros(d, dev)
-            ops.colsum(dz1, dob)
             dz1p = m.split(dz1)
-            dow = m.wgrad(dz1p, m.split(attn), n, d, inner)
+            dow = m.wgrad(dz1p, m.split(attn), n, d, inner, bias_grad=dob, dy=dz1)
             dattn = m.dgrad(dz1p, n, d, out_w)
         else:
             dow, dob, dattn = None, None, dx1
@@ -347,10 +340,9 @@ class LinearFn(torch.autograd.Function):
         dyp = m.split(dy)
         s_w, s_b = _Sink(ctx.params[0], (N, K), dy.device), _Sink(ctx.params[1], (N,), dy.device)
         if s_w.direct:
-            m.wgrad(dyp, m.split(x), M, N, K, out=s_w.buf, accumulate=True)
+            m.wgrad(dyp, m.split(x), M, N, K, out=s_w.buf, accumulate=True, bias_grad=s_b.zeros(), dy=dy)
         else:
-            s_w.buf = m.wgrad(dyp, m.split(x), M, N, K)
-        ops.colsum(dy, s_b.zeros())
+            s_w.buf = m.wgrad(dyp, m.split(x), M, N, K, bias_grad=s_b.zeros(), dy=dy)
         dx = m.dgrad(dyp, M, N, w) if ctx.needs_input_grad[1] else None
         return None, dx, s_w.result(), s_b.result()
 
@@ -421,10 +413,9 @@ class MlpFn(torch.autograd.Function):
             dprep = m.split(dpre)
             s_w, s_b = _Sink(ctx.params[0][i], (N, K), dy.device), _Sink(ctx.params[1][i], (N,), dy.device)
             if s_w.direct:
-                m.wgrad(dprep, m.split(inp), M, N, K, out=s_w.buf, accumulate=True)
+                m.wgrad(dprep, m.split(inp), M, N, K, out=s_w.buf, accumulate=True, bias_grad=s_b.zeros(), dy=dpre)
             else:
-                s_w.buf = m.wgrad(dprep, m.split(inp), M, N, K)
-            ops.colsum(dpre, s_b.zeros())
+                s_w.buf = m.wgrad(dprep, m.split(inp), M, N, K, bias_grad=s_b.zeros(), dy=dpre)
             dws[i], dbs[i] = s_w.result(), s_b.result()
             if i > 0:
                 dpre = m.dgrad(dprep, M, N, ws[i], relu_mask=ys[i - 1] if acts[i - 1] == ACT_RELU else None,

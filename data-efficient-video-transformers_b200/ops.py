@@ -7,6 +7,7 @@ Precision modes (``Mode``):
   "fp32": activations fp32; every GEMM operand is split into two bf16 planes (hi + lo) and the tensor
           cores run hi*hi + hi*lo + lo*hi — the "fp32-accumulate" parity mode (1e-3 tolerance).
 """
+import os
 import weakref
 
 import torch
@@ -56,9 +57,9 @@ def _rowmajor(t):
 def gemm(a, b, m, n, k, *, a_lo=None, b_lo=None, a_mn=False, b_mn=False, lda=None, ldb=None, bias=None,
          act=ACT_NONE, alpha=1.0, residual=None, relu_mask=None, gelu_gate=None, dropout_p=0.0, seed=0,
          out_f32=None, out_bf16=None, out_bf16_lo=None, out_preact=None, splits=1, atomic=False,
-         ln_in=None, ln_res=None, stats_out=None, ln_dim=0, ln_eps=1e-5):
-    """``ln_in=(stats, c)`` / ``ln_res=(stats, gamma, beta)`` / ``stats_out``: the LayerNorm-folded inference epilogues (see
-    tvt_gemm_args in include/tvt.h)."""
+         ln_in=None, ln_res=None, stats_out=None, ln_dim=0, ln_eps=1e-5, a_rowsum=None):
+    """``ln_in=(stats, c)`` / ``ln_res=(stats, gamma, beta)`` / ``stats_out``: the LayerNorm-folded inference epilogues;
+    ``a_rowsum`` [m] fp32 += sum over k of A (the bias gradient inside a wgrad GEMM) - see tvt_gemm_args in include/tvt.h."""
     _cuda(a, b, a_lo, b_lo, bias, residual, relu_mask, gelu_gate, out_f32, out_bf16, out_bf16_lo, out_preact)
     g = capi.GemmArgs()
     g.a, g.a_lo, g.b, g.b_lo = _p(a), _p(a_lo), _p(b), _p(b_lo)
@@ -91,11 +92,26 @@ def gemm(a, b, m, n, k, *, a_lo=None, b_lo=None, a_mn=False, b_mn=False, lda=Non
         _cuda(stats_out)
         g.stats_out = _p(stats_out)
     g.ln_dim, g.ln_eps = ln_dim, ln_eps
+    if a_rowsum is not None:
+        _cuda(a_rowsum)
+        g.a_rowsum = _p(a_rowsum)
     capi.call("tvt_gemm", g, _stream())
 
 
 def ln_fold_supported(m, n, k):
     return bool(capi.load().tvt_gemm_ln_fold_supported(m, n, k))
+
+
+FUSE_BIAS_GRAD = os.environ.get("TVT_FUSE_BIAS_GRAD", "1") != "0"   # bias gradients inside the wgrad GEMMs (tvt_gemm_args.a_rowsum)
+_rowsum_ok = {}
+
+
+def rowsum_supported(m, n, k, splits):
+    key = (m, n, k, splits)
+    r = _rowsum_ok.get(key)
+    if r is None:
+        r = _rowsum_ok[key] = bool(capi.load().tvt_gemm_rowsum_supported(m, n, k, splits))
+    return r
 
 
 def split_f32(x, hi, lo=None):
@@ -329,15 +345,25 @@ class Mode:
         return dx
 
     # dW[N,K] = dy[M,N]^T x[M,K]  (fp32, split-K over the token dimension when the tile grid is small)
-    def wgrad(self, dyp, xp, M, N, K, out=None, accumulate=False):
-        """dW[N, K] = dY^T X.  ``accumulate=True`` adds into ``out`` (fp32 atomics) instead of overwriting it."""
+    def wgrad(self, dyp, xp, M, N, K, out=None, accumulate=False, bias_grad=None, dy=None):
+        """dW[N, K] = dY^T X.  ``accumulate=True`` adds into ``out`` (fp32 atomics) instead of overwriting it.
+        ``bias_grad`` [N] fp32 (zeroed or accumulating) += colsum(dY): inside this GEMM when the kernel selection allows it
+        (bf16 mode, split-K / accumulating launch on the CTA-pair tiles), else by the column-sum kernel over ``dy`` (the
+        unsplit gradient tensor)."""
         splits = pick_splits(((N + 127) // 128) * ((K + 255) // 256), (M + 63) // 64)
         if out is None:
             out = (torch.zeros if splits > 1 else torch.empty)(N, K, dtype=torch.float32, device=dyp[0].device)
         elif splits > 1 and not accumulate:
             out.zero_()
+        atomic = splits > 1 or accumulate
+        # measured (tools/wgrad_time.py): the N = 16 row-sum MMAs cost ~19 % of the GEMM, the column-sum kernel one read of dY:
+        # fused wins while in_features <= ~1200 (and always saves a launch)
+        fused = (bias_grad is not None and FUSE_BIAS_GRAD and atomic and dyp[1] is None and K <= 1024
+                 and rowsum_supported(N, K, M, splits))
+        if bias_grad is not None and not fused:
+            colsum(dy if dy is not None else dyp[0], bias_grad)
         gemm(dyp[0], xp[0], N, K, M, a_lo=dyp[1], b_lo=xp[1], a_mn=True, b_mn=True, lda=_rowmajor(dyp[0]),
-             ldb=_rowmajor(xp[0]), out_f32=out, splits=splits, atomic=splits > 1 or accumulate)
+             ldb=_rowmajor(xp[0]), out_f32=out, splits=splits, atomic=atomic, a_rowsum=bias_grad if fused else None)
         return out
 
 

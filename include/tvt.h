@@ -141,12 +141,19 @@ typedef struct {
   int64_t ln_dim;
   float ln_eps;
   int32_t reserved;
+  /* ---- bias gradient inside the weight-gradient GEMM: dW = dY^T X is this GEMM with A = dY (MN-major), so the bias gradient
+   * colsum(dY) = A . 1 is the row sum of the A operand over the contraction.  a_rowsum [m] fp32 receives += sum_k A[m, k] (atomics,
+   * like out_f32): one extra N = 16 tensor-core MMA per k-step against a tile of ones, no second pass over dY.  Needs atomic_out,
+   * single bf16 planes, both operands MN-major and the CTA-pair tiles: ask tvt_gemm_rowsum_supported(m, n, k, splits) first. */
+  float* a_rowsum;
 } tvt_gemm_args;
 
 TVT_API int tvt_gemm(const tvt_gemm_args* args, void* stream);
 /* 1 when tvt_gemm would run this bf16 forward GEMM on the tiles that carry the LayerNorm-folded epilogues (ln_* fields), else 0:
  * callers choose between the folded inference path and LayerNorm as a kernel of its own with it (host-only, no launch). */
 TVT_API int tvt_gemm_ln_fold_supported(int64_t m, int64_t n, int64_t k);
+/* 1 when tvt_gemm_args.a_rowsum is available for this [m, n, k] accumulating (atomic_out) GEMM with `splits` k-splits. */
+TVT_API int tvt_gemm_rowsum_supported(int64_t m, int64_t n, int64_t k, int32_t splits);
 
 
 /* ------------------------------------------------------------------------------------------------

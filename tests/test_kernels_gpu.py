@@ -72,6 +72,35 @@ def test_gemm_dgrad_wgrad_layouts(tvt):
     assert_close(dw, dy.float().t() @ x.float(), 1e-5, "wgrad split-K")
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(33024, 3072, 768, 2), (33024, 2304, 768, 8), (2112, 1536, 512, 4), (4160, 512, 512, 1), (1000, 264, 520, 3)])
+def test_gemm_wgrad_with_fused_bias_gradient(tvt, M, N, K, splits):
+    """tvt_gemm_args.a_rowsum: colsum(dY) out of the weight-gradient GEMM itself (one extra N = 16 MMA per k-step against ones)
+    = the bias gradient torch's Linear backward computes with a separate reduction (aten::sum over the token dimension)."""
+    # 1e-4: the TMEM accumulator truncates (round toward zero) once per MMA, ~2e-5 over a 16 512-token chain with a non-zero mean
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dy = _bf(torch.randn(M, N, device=_dev(), generator=g) + 0.25)
+    x = _bf(torch.randn(M, K, device=_dev(), generator=g))
+    if not tvt.rowsum_supported(N, K, M, splits):
+        with pytest.raises(Exception, match="a_rowsum"):
+            tvt.gemm(dy, x, N, K, M, a_mn=True, b_mn=True, out_f32=torch.zeros(N, K, device=_dev()), splits=splits, atomic=True,
+                     a_rowsum=torch.zeros(N, device=_dev()))
+        pytest.skip("kernel selection does not put this shape on the CTA-pair tiles: Mode.wgrad uses tvt_colsum for it")
+    dw, db = torch.zeros(N, K, device=_dev()), torch.zeros(N, device=_dev())
+    tvt.gemm(dy, x, N, K, M, a_mn=True, b_mn=True, out_f32=dw, splits=splits, atomic=True, a_rowsum=db)
+    assert_close(dw, dy.float().t() @ x.float(), 1e-4, "wgrad with row sums")
+    assert_close(db, dy.float().sum(0), 1e-4, "bias gradient from the wgrad GEMM")
+    # accumulating launch (DDP gradient sinks): both outputs add
+    tvt.gemm(dy, x, N, K, M, a_mn=True, b_mn=True, out_f32=dw, splits=splits, atomic=True, a_rowsum=db)
+    assert_close(db, 2 * dy.float().sum(0), 1e-4, "bias gradient accumulates")
+    assert_close(dw, 2 * (dy.float().t() @ x.float()), 1e-4, "wgrad accumulates")
+    # Mode.wgrad picks the fused path by itself and agrees with the column-sum kernel
+    m = tvt.Mode("bf16")
+    db2, db3 = torch.zeros(N, device=_dev()), torch.zeros(N, device=_dev())
+    m.wgrad((dy, None), (x, None), M, N, K, bias_grad=db2, dy=dy)
+    tvt.colsum(dy, db3)
+    assert_close(db2, db3, 1e-4, "Mode.wgrad bias gradient vs tvt_colsum")
+
+
 def test_gemm_fused_backward_epilogue(tvt):
     """dgrad with ReLU mask + dropout regeneration + residual: the linear2 -> linear1 hop of the FFN backward."""
     M, N, K = 512, 256, 1024

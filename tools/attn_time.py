@@ -1,0 +1,29 @@
+"""Times the C5 self-attention forward / backward launches back to back on distinct inputs (several buffers, so the L2 does not
+hold the next call's operands), CUDA events.  Usage: python tools/attn_time.py [dropout_p]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, tvt_b200
+from tvt_b200 import ops
+p = float(sys.argv[1]) if len(sys.argv) > 1 else 0.0
+B, S, d, H = 256, 129, 768, 12
+n = B * S
+g = torch.Generator(device="cuda").manual_seed(0)
+NB = 6   # 6 x 152 MB of qkv > the 126 MB L2
+qkvs = [torch.randn(n, 3 * d, device="cuda", generator=g).to(torch.bfloat16) for _ in range(NB)]
+do = torch.randn(n, d, device="cuda", generator=g).to(torch.bfloat16)
+dqkv = torch.empty_like(qkvs[0])
+def fwd(q): return ops.attention_fwd(q[:, :d], q[:, d:2 * d], q[:, 2 * d:], B, H, S, S, 64, 0.125, dropout_p=p, seed=7)
+def bwd(q, o, lse): ops.attention_bwd(q[:, :d], q[:, d:2 * d], q[:, 2 * d:], o, do, lse, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, H, S, S, 64, 0.125, dropout_p=p, seed=7)
+outs = [fwd(q) for q in qkvs]
+for q, (o, lse) in zip(qkvs, outs): bwd(q, o, lse)
+torch.cuda.synchronize()
+def timed(fn, reps=20):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(reps):
+        for i in range(NB): fn(i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * NB)
+tf = timed(lambda i: fwd(qkvs[i]))
+tb = timed(lambda i: bwd(qkvs[i], *outs[i]))
+print(f"attention S=129 B=256 H=12 p={p}: fwd {tf:.1f} us  bwd {tb:.1f} us  (env TU={os.environ.get('TVT_ATTN_TU','1')} PF={os.environ.get('TVT_ATTN_FWD_PREFETCH','1')})")

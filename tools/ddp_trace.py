@@ -45,6 +45,26 @@ if rank == 0:
         covered = min(covered, t - s)
         tot += t - s; cov_tot += covered
         print(f"allreduce {i:2d}: {(s - t0) / 1e3:8.3f} -> {(t - t0) / 1e3:8.3f} ms  ({(t - s) / 1e3:6.3f} ms, {covered / (t - s) * 100:5.1f} % under compute kernels)  {e.name[:60]}")
+    # does a compute kernel run longer when an all-reduce kernel shares the GPU with it?  Kernels are keyed by (name, position in
+    # the repeating per-layer pattern is unknown here, so:) name + duration cluster: the reference is the median of the same-name
+    # kernels that did NOT overlap an all-reduce and lie within +-35 % of it.
+    import json, statistics
+    recs = []
+    for c in comp:
+        s, t = c.time_range.start, c.time_range.end
+        ov = sum(max(0.0, min(t, e.time_range.end) - max(s, e.time_range.start)) for e in nccl)
+        recs.append({"name": c.name, "start_us": s - t0, "dur_us": t - s, "nccl_overlap_us": ov})
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump({"compute": recs, "nccl": [{"start_us": e.time_range.start - t0, "dur_us": e.time_range.end - e.time_range.start} for e in nccl]},
+              open("gpurun_out/ddp_trace_kernels.json", "w"))
+    excess = 0.0; n_ov = 0
+    for r in recs:
+        if r["nccl_overlap_us"] <= 0: continue
+        ref = [q["dur_us"] for q in recs if q["name"] == r["name"] and q["nccl_overlap_us"] <= 0 and 0.65 * r["dur_us"] <= q["dur_us"] <= 1.0 * r["dur_us"] + 1e-9]
+        if len(ref) >= 2:
+            excess += r["dur_us"] - statistics.median(ref); n_ov += 1
+    print(f"# compute kernels overlapping an all-reduce: {sum(1 for r in recs if r['nccl_overlap_us'] > 0)}; against the median of same-name non-overlapped kernels "
+          f"({n_ov} with a reference) they ran {excess / 1e3:.3f} ms longer in total")
     last_nccl_end = max(e.time_range.end for e in nccl) if nccl else last_bwd_end
     print(f"# all-reduce kernel time {tot / 1e3:.3f} ms, {cov_tot / tot * 100 if tot else 0:.1f} % of it concurrent with compute kernels")
     print(f"# exposed: the last all-reduce ends {(last_nccl_end - last_bwd_end) / 1e3:.3f} ms after the last backward kernel (the optimizer waits for it)")
