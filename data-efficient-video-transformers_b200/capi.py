@@ -37,7 +37,7 @@ class GemmArgs(C.Structure):
 class LayerNormFwdArgs(C.Structure):
     _fields_ = [("x", vp), ("cls", vp), ("pe", vp), ("gamma", vp), ("beta", vp), ("y", vp), ("pre", vp),
                 ("mean", vp), ("rstd", vp), ("rows", i64), ("d", i64), ("seq_len", i64), ("dtype", i32),
-                ("eps", f32), ("dropout_p", f32), ("dropout_seed", u64)]
+                ("eps", f32), ("dropout_p", f32), ("dropout_seed", u64), ("y_seq", i64), ("y_pitch", i64)]
 
 
 class LayerNormBwdArgs(C.Structure):

@@ -21,6 +21,8 @@ struct FwdParams {
   long long rows; int d; int S;  // S > 0 selects embed mode (rows = B * S)
   float eps;
   float dropout_scale; unsigned dropout_thr16; unsigned long long dropout_seed; const unsigned long long* seed_src;
+  int y_seq; long long y_pitch;   // ring kernels, optional: output row r goes to y + (r / y_seq) * y_pitch + (r % y_seq) * d elements
+                      // (the rows of one clip land inside a wider per-clip block: no concatenation pass afterwards)
   int reverse;        // ring kernels: walk the rows from the LAST pair to the first.  The producer (a GEMM epilogue) has just
                       // written these rows in ascending order through an L2 smaller than its traffic, so the rows written last
                       // are the ones still resident: reading them first turns DRAM reads into L2 hits
@@ -271,6 +273,12 @@ __global__ void __launch_bounds__(kRingWarps * 32) ln_fwd_ring_kernel(const FwdP
       }
     }
     T* dst = reinterpret_cast<T*>(p.y) + 2 * q * p.d;
+    T* dst1 = dst + p.d;
+    if (p.y_seq > 0) {
+      const long long r0 = 2 * q, r1 = 2 * q + 1;
+      dst = reinterpret_cast<T*>(p.y) + (r0 / p.y_seq) * p.y_pitch + (r0 % p.y_seq) * p.d;
+      dst1 = reinterpret_cast<T*>(p.y) + (r1 / p.y_seq) * p.y_pitch + (r1 % p.y_seq) * p.d;
+    }
     const bool two = 2 * q + 1 < p.rows;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) ln_fwd_ring_kernel(const FwdP
           }
         }
         Vec16<T>::store(dst + col, o0);
-        if (two) Vec16<T>::store(dst + p.d + col, o1);
+        if (two) Vec16<T>::store(dst1 + col, o1);
       }
     }
     if (++slot == kRing) { slot = 0; parity ^= 1; }
@@ -731,6 +739,7 @@ extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) 
   p.reverse = ln_reverse;
   p.x = a->x; p.cls = a->cls; p.pe = a->pe; p.gamma = a->gamma; p.beta = a->beta; p.y = a->y; p.pre = a->pre;
   p.mean = a->mean; p.rstd = a->rstd; p.rows = a->rows; p.d = (int)a->d; p.S = (int)a->seq_len; p.eps = a->eps;
+  p.y_seq = (int)a->y_seq; p.y_pitch = a->y_pitch;
   if (a->dropout_p > 0.0f) {
     p.dropout_thr16 = (unsigned)(a->dropout_p * 65536.0f + 0.5f);
     p.dropout_scale = 65536.0f / (65536.0f - (float)p.dropout_thr16);
@@ -740,6 +749,11 @@ extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // plain rows of up to 4 chunks (d <= 1024 bf16 / 512 fp32): bulk-copy ring kernel; embed mode and wider rows: register-prefetch kernel
   const int vec = a->dtype == TVT_F32 ? 4 : 8;
+  if (a->y_seq != 0) {
+    TVT_REQUIRE(a->y_seq > 0 && a->rows % a->y_seq == 0 && a->y_pitch >= a->y_seq * a->d && a->y_pitch % 8 == 0,
+                "tvt_layernorm_fwd: y_seq must divide rows and y_pitch (elements, multiple of 8) must hold y_seq rows");
+    TVT_REQUIRE(a->seq_len == 0 && p.d <= 4 * 32 * vec, "tvt_layernorm_fwd: the blocked output layout (y_seq) is built for plain rows of d <= %d", 4 * 32 * vec);
+  }
   if (a->seq_len == 0 && p.d <= 4 * 32 * vec)
     return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::FwdRingLauncher>(p, p.d, s)
                                : ln::dispatch_chunks<__nv_bfloat16, ln::FwdRingLauncher>(p, p.d, s);

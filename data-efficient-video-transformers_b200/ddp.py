@@ -8,6 +8,7 @@ wgrad kernels' outputs are accumulated by autograd straight into the communicati
 filled in reverse registration order (the order backward produces gradients).  Works with any
 torch.distributed backend (NCCL on GPUs; gloo in the CPU tests of the bucketing logic).
 """
+import os
 import weakref
 
 import torch
@@ -51,6 +52,9 @@ class GradBucketReducer:
         self.group = process_group
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        # measurement knob (bench.py records it): 1 = never issue the all-reduces, i.e. N independent replicas in lockstep - the
+        # difference to a normal run is the whole cost of gradient communication, interference with backward included
+        self.dry_run = os.environ.get("TVT_DDP_DRY_RUN", "0") == "1"
         self.buckets = []          # list of dict(flat, params, pending, handle)
         self._index = {}
         self._uses = {}            # id(param) -> direct-sink uses registered by forward and not yet reported done
@@ -108,7 +112,7 @@ class GradBucketReducer:
             return
         b["seen"].add(id(p))
         b["pending"] -= 1
-        if b["pending"] == 0 and self.world > 1:
+        if b["pending"] == 0 and self.world > 1 and not self.dry_run:
             # async: NCCL's stream waits on the producer stream, backward keeps going on the compute stream
             b["handle"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
@@ -116,7 +120,7 @@ class GradBucketReducer:
         """Wait for every bucket, reduce the ones whose hooks never fired (unused params), average
         (unless ``average=False``: FlatOptimizer fuses the 1 / world scaling into its step kernel)."""
         for b in self.buckets:
-            if self.world > 1:
+            if self.world > 1 and not self.dry_run:
                 if b["handle"] is None:
                     b["handle"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
                 b["handle"].wait()

@@ -58,14 +58,16 @@ def _fold_ok(mode, enc, tokens, training):
     return True
 
 
-def run_encoder_folded(mode, enc, tokens, batch, attn_impl=0):
+def run_encoder_folded(mode, enc, tokens, batch, attn_impl=0, out=None):
     """Inference-only post-norm encoder stack WITHOUT LayerNorm kernels (the frozen teacher, evaluation): a layer's two
     LayerNorm outputs are never materialised.  The GEMM that writes a pre-norm tensor y (out-proj + residual, FFN2 + residual)
     accumulates each row's (sum, sum of squares) in its epilogue; the GEMMs that consume LN(y) as their A operand (FFN1, the next
     layer's packed QKV projection) run on y itself with gamma folded into the weight and the per-row mean / rstd applied in
     their epilogue; the GEMMs that add LN(y) as a residual recompute it from y in theirs (tvt_gemm_args.ln_*).  Only the last
     layer's output is normalised by the LayerNorm kernel, for the consumers outside the stack.
-    torch/nn/modules/transformer.py:952-982 is the arithmetic being rearranged."""
+    torch/nn/modules/transformer.py:952-982 is the arithmetic being rearranged.
+    ``out=(buf [B, n_blocks * S, d], block)``: the final LayerNorm writes its rows into that block of a wider per-clip buffer
+    (ops.layernorm_fwd) - how FusionTransformer lays the memory experts' tokens side by side without a concatenation pass."""
     import math
     n, d = tokens.shape
     L = len(enc.layers)
@@ -106,12 +108,22 @@ def run_encoder_folded(mode, enc, tokens, batch, attn_impl=0):
                  ln_res=(st1, layer.norm1.weight, layer.norm1.bias), ln_dim=d, ln_eps=eps)
         prev = (y2, st2, layer.norm2)
     y2, _, nrm = prev
-    out, _, _ = ops.layernorm_fwd(y2, nrm.weight, nrm.bias, nrm.eps, save_stats=False)
-    return out
+    res, _, _ = ops.layernorm_fwd(y2, nrm.weight, nrm.bias, nrm.eps, save_stats=False, out=out)
+    return res
 
 
-def run_encoder(mode, enc, tokens, batch, training, attn_impl=0):
-    """Apply every layer of an nn.TransformerEncoder container to batch-major tokens [B*S, d]."""
+def blocked_output_ok(mode, enc, tokens, training):
+    """True when run_encoder(..., out=...) can write its result straight into a block of a wider buffer."""
+    return FOLD_LAYERNORM and enc.norm is None and tokens.shape[1] <= 1024 and _fold_ok(mode, enc, tokens, training)
+
+
+def run_encoder(mode, enc, tokens, batch, training, attn_impl=0, out=None):
+    """Apply every layer of an nn.TransformerEncoder container to batch-major tokens [B*S, d].
+    ``out``: see run_encoder_folded (only when blocked_output_ok(...) holds)."""
+    if out is not None:
+        if not blocked_output_ok(mode, enc, tokens, training):
+            raise TvtError("run_encoder: blocked output needs the LayerNorm-folded inference path")
+        return run_encoder_folded(mode, enc, tokens, batch, attn_impl, out=out)
     if FOLD_LAYERNORM and _fold_ok(mode, enc, tokens, training):
         tokens = run_encoder_folded(mode, enc, tokens, batch, attn_impl)
         if enc.norm is not None:

@@ -11,7 +11,7 @@ from .. import ops
 from ..compat import LightningModule
 from ..functions import (DistillLossFn, EmbedFn, EncoderLayerFn, HeadLinearFn, LayerCfg, LayerNormFn, LinearFn,
                          PyramidHeadFn, ReadoutFn)
-from .common import make_encoder, run_encoder, to_act
+from .common import blocked_output_ok, make_encoder, run_encoder, to_act
 from .TPN import Reasoning
 from .transformer import PositionalEncoding
 
@@ -49,13 +49,23 @@ class ExpertStream(nn.Module):
         self.cls = nn.Parameter(torch.rand(1, batch_size, d))
         self.transformer_encoder = make_encoder(d, nhead, nhid, dropout, nlayers)
 
-    def tokens_forward(self, mode, x):
+    def tokens_forward(self, mode, x, out=None):
+        """``out=(buf [B, n_blocks * S, d], block)`` (inference only): the tokens are ALSO laid into that block of a wider per-clip
+        buffer - by the last LayerNorm itself on the LayerNorm-folded path, else by one strided copy."""
         B, T, D = x.shape
         xa = to_act(mode, x).view(B * T, D)
         feat = LinearFn.apply(mode, xa, self.expert_encoder.weight, self.expert_encoder.bias).view(B, T, -1)
         p = self.position_encoder.dropout.p if self.training else 0.0
         tok = EmbedFn.apply(mode, feat, self.cls, self.position_encoder.pe, self.norm.weight, self.norm.bias, p)
-        return run_encoder(mode, self.transformer_encoder, tok, B, self.training)
+        if out is None:
+            return run_encoder(mode, self.transformer_encoder, tok, B, self.training)
+        if blocked_output_ok(mode, self.transformer_encoder, tok, self.training):
+            return run_encoder(mode, self.transformer_encoder, tok, B, self.training, out=out)
+        res = run_encoder(mode, self.transformer_encoder, tok, B, self.training)
+        buf, blk = out
+        S = T + 1
+        buf[:, blk * S:(blk + 1) * S].copy_(res.view(B, S, -1))
+        return res
 
 
 class FusionTransformer(LightningModule):
@@ -83,9 +93,22 @@ class FusionTransformer(LightningModule):
         m = self.mode
         B, T = experts[0].shape[0], experts[0].shape[1]
         S = T + 1
-        toks = [s.tokens_forward(m, x) for s, x in zip(self.streams, experts)]
+        E = len(self.streams)
+        mem = None
+        if self.fusion == "cross" and E > 2 and not torch.is_grad_enabled():
+            # inference: every memory expert's last LayerNorm writes its tokens straight into its block of the per-clip memory
+            # [B, (E - 1) * S, d] (transformer.py:110-121 concatenates them): no torch.cat pass (101 MB per C5 step)
+            d = self.streams[0].expert_encoder.out_features
+            buf = torch.empty(B, (E - 1) * S, d, dtype=m.dtype, device=experts[0].device)
+            toks = [self.streams[0].tokens_forward(m, experts[0])]
+            toks += [s.tokens_forward(m, x, out=(buf, e)) for e, (s, x) in enumerate(zip(self.streams[1:], experts[1:]))]
+            mem = buf.view(-1, d)
+        else:
+            toks = [s.tokens_forward(m, x) for s, x in zip(self.streams, experts)]
         if self.fusion == "cross" and len(toks) > 1:
-            if len(toks) > 2:   # memory = other experts' tokens concatenated along the sequence, per clip
+            if mem is not None:
+                pass
+            elif len(toks) > 2:   # memory = other experts' tokens concatenated along the sequence, per clip
                 d = toks[0].shape[1]
                 mem = torch.cat([t.view(B, S, d) for t in toks[1:]], dim=1).reshape(-1, d)
             else:

@@ -368,15 +368,29 @@ class Mode:
 
 
 # ------------------------------------------------------------------------------------------ LayerNorm
-def layernorm_fwd(x, gamma, beta, eps=1e-5, *, save_stats=True):
+def layernorm_fwd(x, gamma, beta, eps=1e-5, *, save_stats=True, out=None):
+    """``out=(buf [B, n_blocks * S, d], block)``: write the rows of clip b as rows [block * S, (block + 1) * S) of buf[b] (the
+    blocked output of tvt_layernorm_fwd) and return that strided view [B, S, d] instead of a dense [rows, d] tensor."""
     _cuda(x, gamma, beta)
     rows, d = x.shape
-    y = torch.empty_like(x)
+    y_seq = y_pitch = 0
+    if out is not None:
+        buf, block = out
+        _cuda(buf)
+        B, tot, d2 = buf.shape
+        S = rows // B
+        if d2 != d or rows != B * S or tot % S or not 0 <= block < tot // S or not buf.is_contiguous() or buf.dtype != x.dtype:
+            raise TvtError("layernorm_fwd: out buffer does not match [B, n_blocks * S, d]")
+        y = buf[:, block * S:(block + 1) * S]
+        y_seq, y_pitch = S, tot * d
+    else:
+        y = torch.empty_like(x)
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     a = capi.LayerNormFwdArgs()
     a.x, a.gamma, a.beta, a.y, a.mean, a.rstd = _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd)
     a.rows, a.d, a.seq_len, a.dtype, a.eps = rows, d, 0, _dt(x), eps
+    a.y_seq, a.y_pitch = y_seq, y_pitch
     capi.call("tvt_layernorm_fwd", a, _stream())
     return y, mean, rstd
 

@@ -181,6 +181,10 @@ typedef struct {
   float eps;
   float dropout_p;    /* embed mode only: dropout after the positional encoding */
   uint64_t dropout_seed;
+  /* optional blocked output (plain mode, d <= 1024 bf16 / 512 fp32): row r is written to y + (r / y_seq) * y_pitch + (r % y_seq) * d
+   * elements, i.e. the y_seq rows of one clip land inside a wider per-clip block.  Builds the cross-attention memory of
+   * src/models/transformer.py:110-121 (the other experts' tokens side by side) without a concatenation pass.  0 = dense [rows, d]. */
+  int64_t y_seq, y_pitch;
 } tvt_layernorm_fwd_args;
 TVT_API int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* args, void* stream);
 

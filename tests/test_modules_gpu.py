@@ -742,3 +742,53 @@ def test_layernorm_free_inference_stack(api, d, H, ff, L, B, T):
     # with autograd recording, the stack must take the differentiable path
     out = common.run_encoder(mode, enc, tok.clone().requires_grad_(True), B, False)
     assert out.requires_grad
+
+
+def test_cross_memory_built_without_concatenation(api):
+    """Inference through a 3-expert cross-attention FusionTransformer (src/models/transformer.py:110-121): the memory experts' last
+    LayerNorm writes its tokens straight into its block of the per-clip memory (tvt_layernorm_fwd blocked output).  Same bits as
+    laying the dense tokens into the buffer by a copy, same launches minus the copies, and the bf16 bar against the differentiable
+    (torch.cat) path."""
+    import tvt_b200
+    from tvt_b200 import hostapi, ops
+    from tvt_b200.hostapi import fusion
+    torch.manual_seed(7)
+    B, T, d = 256, 32, 512
+    model = hostapi.FusionTransformer((2048, 1024, 128), d=d, nhead=8, nhid=2048, nlayers=2, dropout=0.0, batch_size=B, frames=T,
+                                      n_classes=15, fusion="cross", precision="bf16").to(DEV).eval()
+    gen = torch.Generator().manual_seed(5)
+    xs = [torch.randn(B, T, D, generator=gen).to(DEV) for D in (2048, 1024, 128)]
+    with torch.no_grad():
+        model(xs)                                                # weight conversions out of the launch counts
+        l0 = tvt_b200.capi.launches
+        blocked = model(xs)[0]
+        l1 = tvt_b200.capi.launches
+        ok = fusion.blocked_output_ok
+        fusion.blocked_output_ok = lambda *a, **k: False         # same forward, tokens copied into the buffer afterwards
+        try:
+            copied = model(xs)[0]
+        finally:
+            fusion.blocked_output_ok = ok
+        l2 = tvt_b200.capi.launches
+    assert torch.equal(blocked, copied), "blocked LayerNorm output differs from dense output + copy"
+    assert l1 - l0 == l2 - l1                                   # same tvt launches; the copy path adds two ATen copies on top
+    with torch.enable_grad():
+        ref = model(xs)[0]                                       # differentiable path: EncoderLayerFn per layer + torch.cat
+    assert ref.requires_grad
+    assert_close(blocked, ref.detach(), 2e-2, "blocked-memory inference vs differentiable path")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_layernorm_blocked_output(api, dtype):
+    from tvt_b200 import ops
+    B, S, d, blocks = 6, 33, 256, 3
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(B * S, d, device=DEV, generator=g).to(dtype)
+    gamma, beta = torch.rand(d, device=DEV, generator=g) + 0.5, torch.randn(d, device=DEV, generator=g)
+    dense, _, _ = ops.layernorm_fwd(x, gamma, beta)
+    buf = torch.full((B, blocks * S, d), 7.0, device=DEV, dtype=dtype)
+    view, _, _ = ops.layernorm_fwd(x, gamma, beta, out=(buf, 1))
+    assert torch.equal(view.reshape(B * S, d), dense) and torch.equal(buf[:, S:2 * S].reshape(B * S, d), dense)
+    assert bool((buf[:, :S] == 7.0).all()) and bool((buf[:, 2 * S:] == 7.0).all())      # the neighbouring blocks are untouched
+    with pytest.raises(Exception, match="out buffer"):
+        ops.layernorm_fwd(x, gamma, beta, out=(buf[:, :S + 1], 0))
