@@ -53,7 +53,7 @@ struct Params {
 };
 
 static unsigned g_mn_lbo = BK * 128, g_mn_sbo = 1024;
-static int g_dbg = 0;
+static int g_dbg = [] { const char* e = getenv("TVT_GEMM_DBG"); return e ? atoi(e) : 0; }();   // bring-up bits, see Params::dbg (32 = release.cluster accumulator hand-back)
 static int g_pair = [] { const char* e = getenv("TVT_GEMM_PAIR"); return e ? atoi(e) : 1; }();   // bring-up knob: 0 = never use the CTA-pair kernels
 static long long g_fast_fallbacks = 0;   // fast-path launches that had no exact-stage kernel (see tvt_gemm)
 
@@ -839,7 +839,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (kCta2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA warp waits on it
+        // the leader's MMA warp waits on it.  Default-semantics arrive (mbar_arrive_remote): the hand-back publishes nothing, and the
+        // release.cluster form made every epilogue warp wait for its tile's global stores to drain first (ncu: `membar` among the
+        // top three stalls of every pair kernel) - 0.8 ms of a 44 ms C5 step.  TVT_GEMM_DBG=32 keeps the old form for A/B runs.
+        if constexpr (kCta2) {
+          if (p.dbg & 32) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+          else mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+        }
         else mbar_arrive(smem_u32(&tempty_bar[as]));
       }
       if (++as == C::kAccStages) { as = 0; aphase ^= 1; }

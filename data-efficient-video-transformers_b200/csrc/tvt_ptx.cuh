@@ -190,6 +190,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// Arrive on a (possibly remote) barrier with the DEFAULT semantics (release at CTA scope - the form CUTLASS's ClusterBarrier::arrive
+// uses for a consumer handing a pipeline stage back to a producer in another CTA): for "I am done reading" signals, where nothing
+// this thread wrote to global memory has to become visible to the waiter.  mbar_arrive_cluster's release.cluster makes the thread
+// wait for its outstanding global stores first - an epilogue warp that has just issued a tile's worth of them stalls on it.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 // TMA tile load issued by either CTA of a pair: data lands in this CTA's shared memory, the bytes are counted
 // on `cluster_bar`, a shared::cluster address that may name the leader CTA's barrier
 __device__ __forceinline__ void tma_load_2d_cta2(uint32_t dst_smem, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
