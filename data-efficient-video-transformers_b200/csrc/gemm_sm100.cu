@@ -1039,6 +1039,8 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
   TVT_REQUIRE(!a->bias || al16(a->bias), "tvt_gemm: bias must be 16-byte aligned");
   const long long kb_total = (a->k + gemm::BK - 1) / gemm::BK;
   TVT_REQUIRE(a->splits <= kb_total, "tvt_gemm: more splits (%d) than k-blocks (%lld)", a->splits, kb_total);
+  TVT_REQUIRE(!a->a_rowsum || (a->atomic_out && !a->a_lo && a->a_mn_major && a->b_mn_major && (reinterpret_cast<uintptr_t>(a->a_rowsum) & 3) == 0),
+              "tvt_gemm: a_rowsum needs atomic_out, single bf16 planes and MN-major operands (the wgrad orientation)");
 
   int rc = require_sm100();
   if (rc != TVT_OK) return rc;
@@ -1086,8 +1088,6 @@ extern "C" int tvt_gemm(const tvt_gemm_args* a, void* stream) {
                     !(a->relu_mask && a->mask_dtype == TVT_F32) && !(a->residual && a->relu_mask) && a->n % 32 == 0 &&
                     al32(a->out_bf16, a->ld_bf16);
   if (a->a_rowsum) {
-    TVT_REQUIRE(a->atomic_out && !a->a_lo && a->a_mn_major && a->b_mn_major && (reinterpret_cast<uintptr_t>(a->a_rowsum) & 3) == 0,
-                "tvt_gemm: a_rowsum needs atomic_out, single bf16 planes and MN-major operands (the wgrad orientation)");
     TVT_REQUIRE(tvt_gemm_rowsum_supported(a->m, a->n, a->k, a->splits),
                 "tvt_gemm: a_rowsum is built for the CTA-pair [256 x 256] tiles (ask tvt_gemm_rowsum_supported first)");
     return gemm::launch<256, true, true, 1, gemm::kEpiAtomicSum, true>(a, p, s);

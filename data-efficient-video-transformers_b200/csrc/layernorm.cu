@@ -731,6 +731,12 @@ extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) 
   }
   TVT_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "tvt_layernorm_fwd: dropout_p must be in [0,1)");
   TVT_REQUIRE(a->dropout_p == 0.0f || a->seq_len > 0, "tvt_layernorm_fwd: dropout only applies in embed mode");
+  if (a->y_seq != 0) {
+    const int max_d = 4 * 32 * (a->dtype == TVT_F32 ? 4 : 8);
+    TVT_REQUIRE(a->y_seq > 0 && a->rows % a->y_seq == 0 && a->y_pitch >= a->y_seq * a->d && a->y_pitch % 8 == 0,
+                "tvt_layernorm_fwd: y_seq must divide rows and y_pitch (elements, multiple of 8) must hold y_seq rows");
+    TVT_REQUIRE(a->seq_len == 0 && a->d <= max_d, "tvt_layernorm_fwd: the blocked output layout (y_seq) is built for plain rows of d <= %d", max_d);
+  }
   if (a->rows == 0) return TVT_OK;
   int rc = require_sm100();
   if (rc != TVT_OK) return rc;
@@ -749,11 +755,6 @@ extern "C" int tvt_layernorm_fwd(const tvt_layernorm_fwd_args* a, void* stream) 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // plain rows of up to 4 chunks (d <= 1024 bf16 / 512 fp32): bulk-copy ring kernel; embed mode and wider rows: register-prefetch kernel
   const int vec = a->dtype == TVT_F32 ? 4 : 8;
-  if (a->y_seq != 0) {
-    TVT_REQUIRE(a->y_seq > 0 && a->rows % a->y_seq == 0 && a->y_pitch >= a->y_seq * a->d && a->y_pitch % 8 == 0,
-                "tvt_layernorm_fwd: y_seq must divide rows and y_pitch (elements, multiple of 8) must hold y_seq rows");
-    TVT_REQUIRE(a->seq_len == 0 && p.d <= 4 * 32 * vec, "tvt_layernorm_fwd: the blocked output layout (y_seq) is built for plain rows of d <= %d", 4 * 32 * vec);
-  }
   if (a->seq_len == 0 && p.d <= 4 * 32 * vec)
     return a->dtype == TVT_F32 ? ln::dispatch_chunks<float, ln::FwdRingLauncher>(p, p.d, s)
                                : ln::dispatch_chunks<__nv_bfloat16, ln::FwdRingLauncher>(p, p.d, s);

@@ -74,6 +74,18 @@ def test_validation_needs_no_gpu(capi):
     ln.x = ln.y = ln.gamma = ln.beta = 16
     ln.rows, ln.d = 4, 12
     assert lib.tvt_layernorm_fwd(ctypes.byref(ln), None) == -1
+    # blocked LayerNorm output: y_seq must divide rows and y_pitch must hold y_seq rows
+    ln.rows, ln.d, ln.y_seq, ln.y_pitch = 12, 64, 5, 1024
+    assert lib.tvt_layernorm_fwd(ctypes.byref(ln), None) == -1 and b"y_seq" in lib.tvt_last_error()
+    ln.y_seq, ln.y_pitch = 4, 128
+    assert lib.tvt_layernorm_fwd(ctypes.byref(ln), None) == -1 and b"y_seq" in lib.tvt_last_error()
+    # fused bias gradient: only for accumulating (atomic_out) wgrad-oriented GEMMs
+    g = capi.GemmArgs()
+    g.a, g.b, g.m, g.n, g.k, g.lda, g.ldb, g.splits = 16, 16, 512, 512, 4096, 512, 512, 1
+    g.a_mn_major = g.b_mn_major = 1
+    g.out_f32, g.ld_f32, g.a_rowsum = 16, 512, 16
+    assert lib.tvt_gemm(ctypes.byref(g), None) == -1 and b"a_rowsum" in lib.tvt_last_error()
+    assert lib.tvt_gemm_rowsum_supported(0, 512, 4096, 1) == 0 and lib.tvt_gemm_rowsum_supported(512, 512, 64, 2) == 0
 
 
 def test_product_path_fails_loudly_without_cuda(capi):
