@@ -141,3 +141,38 @@ def test_shared_parameter_direct_sinks_world2():
     for rank in range(world):
         assert torch.allclose(out[rank][0], w.grad, rtol=1e-5, atol=1e-7)
         assert torch.allclose(out[rank][1], head.grad, rtol=1e-5, atol=1e-7)
+
+
+def _dry_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      TVT_DDP_DRY_RUN="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tvt_b200.ddp import GradBucketReducer
+    model = _make_model()
+    red = GradBucketReducer(list(model.parameters()), bucket_bytes=2048, average=False)
+    assert red.dry_run
+    g = torch.Generator().manual_seed(7)
+    x, y = torch.randn(8, 16, generator=g), torch.randn(8, 5, generator=g)
+    red.zero_grad()
+    torch.nn.functional.mse_loss(model(x[rank * 4:(rank + 1) * 4]), y[rank * 4:(rank + 1) * 4]).backward()
+    red.finish()
+    assert all(b["handle"] is None for b in red.buckets)            # no collective was issued
+    out[rank] = [p.grad.clone() for p in model.parameters()]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_dry_run_knob_skips_the_allreduce():
+    """TVT_DDP_DRY_RUN=1 (the measurement knob behind DESIGN section 6's communication-cost number): gradients stay local."""
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_dry_worker, args=(world, port, out), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(7)
+    x, y = torch.randn(8, 16, generator=g), torch.randn(8, 5, generator=g)
+    for rank in range(world):
+        model = _make_model()
+        torch.nn.functional.mse_loss(model(x[rank * 4:(rank + 1) * 4]), y[rank * 4:(rank + 1) * 4]).backward()
+        for a, p in zip(out[rank], model.parameters()):
+            assert torch.allclose(a, p.grad, rtol=1e-6, atol=1e-8)   # each rank's OWN shard gradient, unreduced
