@@ -361,6 +361,8 @@ class Mode:
         fused = (bias_grad is not None and FUSE_BIAS_GRAD and atomic and dyp[1] is None and K <= 1024
                  and rowsum_supported(N, K, M, splits))
         if bias_grad is not None and not fused:
+            if dy is None and dyp[1] is not None:
+                raise TvtError("wgrad: bias_grad in the fp32 mode needs the unsplit gradient tensor (dy=...)")
             colsum(dy if dy is not None else dyp[0], bias_grad)
         gemm(dyp[0], xp[0], N, K, M, a_lo=dyp[1], b_lo=xp[1], a_mn=True, b_mn=True, lda=_rowmajor(dyp[0]),
              ldb=_rowmajor(xp[0]), out_f32=out, splits=splits, atomic=atomic, a_rowsum=bias_grad if fused else None)
